@@ -1,0 +1,319 @@
+/*
+ * fluid_oracle.c — CPU restatement (plain C + OpenMP) of script.js's simulation passes.
+ * TEST INFRASTRUCTURE ONLY — see fluid_oracle.h.  Build: make -C oracle  (-ffp-contract=off).
+ *
+ * Every function is a literal restatement of one GLSL fragment shader of the reference, written
+ * from the shader text, with the operation order of the GLSL expression kept (fp32 is not
+ * associative and the GPU parity tests are bitwise for every pass but splat).
+ * Geometry (baseVertexShader S:440-459): a fragment at cell (i,j) has vUv = ((i+.5)/W,(j+.5)/H)
+ * and vL/vR/vT/vB one texel away; with CLAMP_TO_EDGE (S:1051-1052) an off-grid neighbour of an
+ * edge cell is the edge cell itself.
+ */
+#include "fluid_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+static inline int clampi(int a, int lo, int hi) { return a < lo ? lo : (a > hi ? hi : a); }
+
+int oracle_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+/* S:814-833.  L,R = velocity.y left/right; T,B = velocity.x top/bottom;
+ * vorticity = R - L - T + B; out = 0.5 * vorticity. */
+void oracle_curl(const float* v, float* curl, int W, int H) {
+#pragma omp parallel for schedule(static)
+    for (int j = 0; j < H; ++j) {
+        const int jb = clampi(j - 1, 0, H - 1), jt = clampi(j + 1, 0, H - 1);
+        for (int i = 0; i < W; ++i) {
+            const int il = clampi(i - 1, 0, W - 1), ir = clampi(i + 1, 0, W - 1);
+            const float L = v[2 * ((size_t)j * W + il) + 1];
+            const float R = v[2 * ((size_t)j * W + ir) + 1];
+            const float T = v[2 * ((size_t)jt * W + i) + 0];
+            const float B = v[2 * ((size_t)jb * W + i) + 0];
+            const float vort = ((R - L) - T) + B;
+            curl[(size_t)j * W + i] = 0.5f * vort;
+        }
+    }
+}
+
+/* S:835-866.  force = 0.5*vec2(|T|-|B|, |R|-|L|); force /= length(force)+0.0001;
+ * force *= curl*C; force.y *= -1; velocity += force*dt; clamp to [-1000,1000]. */
+void oracle_vorticity(const float* v, const float* curl, float* vout, int W, int H, float curl_k,
+                      float dt) {
+#pragma omp parallel for schedule(static)
+    for (int j = 0; j < H; ++j) {
+        const int jb = clampi(j - 1, 0, H - 1), jt = clampi(j + 1, 0, H - 1);
+        for (int i = 0; i < W; ++i) {
+            const int il = clampi(i - 1, 0, W - 1), ir = clampi(i + 1, 0, W - 1);
+            const float L = curl[(size_t)j * W + il];
+            const float R = curl[(size_t)j * W + ir];
+            const float T = curl[(size_t)jt * W + i];
+            const float B = curl[(size_t)jb * W + i];
+            const float C = curl[(size_t)j * W + i];
+            float fx = 0.5f * (fabsf(T) - fabsf(B));
+            float fy = 0.5f * (fabsf(R) - fabsf(L));
+            const float len = sqrtf(fx * fx + fy * fy);
+            const float den = len + 0.0001f;
+            fx = fx / den;
+            fy = fy / den;
+            const float s = curl_k * C;
+            fx = fx * s;
+            fy = fy * s;
+            fy = fy * -1.0f;
+            float vx = v[2 * ((size_t)j * W + i) + 0];
+            float vy = v[2 * ((size_t)j * W + i) + 1];
+            vx = vx + fx * dt;
+            vy = vy + fy * dt;
+            vx = fminf(fmaxf(vx, -1000.0f), 1000.0f);
+            vy = fminf(fmaxf(vy, -1000.0f), 1000.0f);
+            vout[2 * ((size_t)j * W + i) + 0] = vx;
+            vout[2 * ((size_t)j * W + i) + 1] = vy;
+        }
+    }
+}
+
+/* S:786-812.  Reflecting walls: the tests vL.x<0, vR.x>1, vT.y>1, vB.y<0 (S:804-807) hold
+ * exactly for i==0, i==W-1, j==H-1, j==0.  div = 0.5*(R - L + T - B). */
+void oracle_divergence(const float* v, float* div, int W, int H) {
+#pragma omp parallel for schedule(static)
+    for (int j = 0; j < H; ++j) {
+        const int jb = clampi(j - 1, 0, H - 1), jt = clampi(j + 1, 0, H - 1);
+        for (int i = 0; i < W; ++i) {
+            const int il = clampi(i - 1, 0, W - 1), ir = clampi(i + 1, 0, W - 1);
+            float L = v[2 * ((size_t)j * W + il) + 0];
+            float R = v[2 * ((size_t)j * W + ir) + 0];
+            float T = v[2 * ((size_t)jt * W + i) + 1];
+            float B = v[2 * ((size_t)jb * W + i) + 1];
+            const float Cx = v[2 * ((size_t)j * W + i) + 0];
+            const float Cy = v[2 * ((size_t)j * W + i) + 1];
+            if (i == 0) L = -Cx;
+            if (i == W - 1) R = -Cx;
+            if (j == H - 1) T = -Cy;
+            if (j == 0) B = -Cy;
+            div[(size_t)j * W + i] = 0.5f * (((R - L) + T) - B);
+        }
+    }
+}
+
+/* S:508-519: gl_FragColor = value * texture2D(uTexture, vUv). */
+void oracle_clear(const float* in, float* out, size_t n, float value) {
+#pragma omp parallel for schedule(static)
+    for (long long k = 0; k < (long long)n; ++k) out[k] = value * in[k];
+}
+
+/* S:868-890: pressure = (L + R + B + T - divergence) * 0.25   (C is fetched but unused). */
+void oracle_jacobi(const float* p, const float* div, float* pout, int W, int H) {
+#pragma omp parallel for schedule(static)
+    for (int j = 0; j < H; ++j) {
+        const float* pc = p + (size_t)j * W;
+        const float* pb = p + (size_t)clampi(j - 1, 0, H - 1) * W;
+        const float* pt = p + (size_t)clampi(j + 1, 0, H - 1) * W;
+        const float* dv = div + (size_t)j * W;
+        float* o = pout + (size_t)j * W;
+        for (int i = 0; i < W; ++i) {
+            const float L = pc[i > 0 ? i - 1 : 0];
+            const float R = pc[i < W - 1 ? i + 1 : W - 1];
+            o[i] = ((((L + R) + pb[i]) + pt[i]) - dv[i]) * 0.25f;
+        }
+    }
+}
+
+void oracle_jacobi_iters(float* p, float* tmp, const float* div, int W, int H, int iters) {
+    float *a = p, *b = tmp;
+    for (int k = 0; k < iters; ++k) {
+        oracle_jacobi(a, div, b, W, H);
+        float* t = a; a = b; b = t; /* pressure.swap() S:1265 */
+    }
+    if (a != p) memcpy(p, a, (size_t)W * H * sizeof(float));
+}
+
+/* S:892-913: velocity.xy -= vec2(R - L, T - B)  (no 1/2 factor, unlike divergence). */
+void oracle_gradient_subtract(const float* p, const float* v, float* vout, int W, int H) {
+#pragma omp parallel for schedule(static)
+    for (int j = 0; j < H; ++j) {
+        const int jb = clampi(j - 1, 0, H - 1), jt = clampi(j + 1, 0, H - 1);
+        for (int i = 0; i < W; ++i) {
+            const int il = clampi(i - 1, 0, W - 1), ir = clampi(i + 1, 0, W - 1);
+            const float L = p[(size_t)j * W + il], R = p[(size_t)j * W + ir];
+            const float T = p[(size_t)jt * W + i], B = p[(size_t)jb * W + i];
+            vout[2 * ((size_t)j * W + i) + 0] = v[2 * ((size_t)j * W + i) + 0] - (R - L);
+            vout[2 * ((size_t)j * W + i) + 1] = v[2 * ((size_t)j * W + i) + 1] - (T - B);
+        }
+    }
+}
+
+/* bilerp of S:758-770:  st = uv/tsize - 0.5; iuv = floor(st); fuv = fract(st);
+ * a,b,c,d = texels (iuv + {.5,1.5}) * tsize fetched NEAREST + CLAMP_TO_EDGE;
+ * mix(mix(a,b,fuv.x), mix(c,d,fuv.x), fuv.y) with GLSL mix(x,y,t) = x*(1-t) + y*t. */
+static inline int texel_index(float f, int n) {
+    /* NEAREST lookup of coordinate (f + .5)*tsize with CLAMP_TO_EDGE == clamp(f, 0, n-1) */
+    if (!(f > 0.0f)) return 0;
+    if (f >= (float)(n - 1)) return n - 1;
+    return (int)f;
+}
+static inline float mixf(float x, float y, float t) { return x * (1.0f - t) + y * t; }
+
+static inline void bilerp(const float* tex, int W, int H, int C, float uvx, float uvy, float tsx,
+                          float tsy, float* out) {
+    const float stx = uvx / tsx - 0.5f, sty = uvy / tsy - 0.5f;
+    const float ix = floorf(stx), iy = floorf(sty);
+    const float fx = stx - ix, fy = sty - iy;
+    const int i0 = texel_index(ix, W), i1 = texel_index(ix + 1.0f, W);
+    const int j0 = texel_index(iy, H), j1 = texel_index(iy + 1.0f, H);
+    const float* a = tex + ((size_t)j0 * W + i0) * C;
+    const float* b = tex + ((size_t)j0 * W + i1) * C;
+    const float* c = tex + ((size_t)j1 * W + i0) * C;
+    const float* d = tex + ((size_t)j1 * W + i1) * C;
+    for (int k = 0; k < C; ++k) out[k] = mixf(mixf(a[k], b[k], fx), mixf(c[k], d[k], fx), fy);
+}
+
+/* S:772-783 (MANUAL_FILTERING branch):
+ *   coord  = vUv - dt * bilerp(uVelocity, vUv, texelSize).xy * texelSize;
+ *   result = bilerp(uSource, coord, dyeTexelSize);
+ *   gl_FragColor = result / (1.0 + dissipation * dt);
+ * texelSize is the SIM texel for both passes (S:1276 is never re-set before S:1292). */
+void oracle_advect(const float* vel, int W, int H, const float* src, float* out, int Ws, int Hs,
+                   int C, float dt, float dissipation) {
+    const float tsx = (float)(1.0 / (double)W), tsy = (float)(1.0 / (double)H);      /* S:1061-1062 */
+    const float dsx = (float)(1.0 / (double)Ws), dsy = (float)(1.0 / (double)Hs);
+    const float decay = 1.0f + dissipation * dt;
+#pragma omp parallel for schedule(static)
+    for (int J = 0; J < Hs; ++J) {
+        const float uvy = ((float)J + 0.5f) / (float)Hs;
+        for (int I = 0; I < Ws; ++I) {
+            const float uvx = ((float)I + 0.5f) / (float)Ws;
+            float vv[2];
+            bilerp(vel, W, H, 2, uvx, uvy, tsx, tsy, vv);
+            const float cx = uvx - (dt * vv[0]) * tsx;
+            const float cy = uvy - (dt * vv[1]) * tsy;
+            float r[4];
+            bilerp(src, Ws, Hs, C, cx, cy, dsx, dsy, r);
+            float* o = out + ((size_t)J * Ws + I) * C;
+            for (int k = 0; k < C; ++k) o[k] = r[k] / decay;
+        }
+    }
+}
+
+/* S:726-744: p = vUv - point; p.x *= aspectRatio; splat = exp(-dot(p,p)/radius)*color;
+ * gl_FragColor = vec4(base.xyz + splat, 1.0).  An RG target keeps .xy only. */
+void oracle_splat(const float* base, float* out, int W, int H, int C, float aspect, float px,
+                  float py, const float* color3, float radius) {
+#pragma omp parallel for schedule(static)
+    for (int j = 0; j < H; ++j) {
+        const float uvy = ((float)j + 0.5f) / (float)H;
+        for (int i = 0; i < W; ++i) {
+            const float uvx = ((float)i + 0.5f) / (float)W;
+            float dx = uvx - px;
+            const float dy = uvy - py;
+            dx = dx * aspect;
+            const float d = dx * dx + dy * dy;
+            const float e = expf(-d / radius);
+            const float* b = base + ((size_t)j * W + i) * C;
+            float* o = out + ((size_t)j * W + i) * C;
+            const int n3 = C < 3 ? C : 3;
+            for (int k = 0; k < n3; ++k) o[k] = b[k] + e * color3[k];
+            if (C == 4) o[3] = 1.0f;
+        }
+    }
+}
+
+/* copyShader S:496-506 drawn into the new FBO while sampling the old texture through its
+ * LINEAR filter (resizeFBO S:1108-1114).  Bilinear is defined as in bilerp above. */
+void oracle_resample(const float* src, int Ws, int Hs, float* dst, int Wd, int Hd, int C) {
+    const float tsx = (float)(1.0 / (double)Ws), tsy = (float)(1.0 / (double)Hs);
+#pragma omp parallel for schedule(static)
+    for (int J = 0; J < Hd; ++J) {
+        const float uvy = ((float)J + 0.5f) / (float)Hd;
+        for (int I = 0; I < Wd; ++I) {
+            const float uvx = ((float)I + 0.5f) / (float)Wd;
+            bilerp(src, Ws, Hs, C, uvx, uvy, tsx, tsy, dst + ((size_t)J * Wd + I) * C);
+        }
+    }
+}
+
+void oracle_round_half(float* a, size_t n) {
+#pragma omp parallel for schedule(static)
+    for (long long k = 0; k < (long long)n; ++k) a[k] = (float)(_Float16)a[k];
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+
+oracle_sim* oracle_sim_create(int W, int H, int Wd, int Hd) {
+    oracle_sim* s = (oracle_sim*)calloc(1, sizeof(*s));
+    s->W = W; s->H = H; s->Wd = Wd; s->Hd = Hd;
+    s->density_dissipation = 1.0f;      /* S:63 */
+    s->velocity_dissipation = 0.2f;     /* S:64 */
+    s->pressure = 0.8f;                 /* S:65 */
+    s->pressure_iterations = 20;        /* S:66 */
+    s->curl = 30.0f;                    /* S:67 */
+    s->splat_radius = 0.25f;            /* S:68 */
+    s->aspect = (float)W / (float)H;
+    const size_t n = (size_t)W * H, nd = (size_t)Wd * Hd;
+    s->v = (float*)calloc(2 * n, 4);   s->v2 = (float*)calloc(2 * n, 4);
+    s->dye = (float*)calloc(4 * nd, 4); s->dye2 = (float*)calloc(4 * nd, 4);
+    s->p = (float*)calloc(n, 4);       s->p2 = (float*)calloc(n, 4);
+    s->div = (float*)calloc(n, 4);     s->curl_f = (float*)calloc(n, 4);
+    /* createFBO clears to clearColor (0,0,0,1) (S:136, S:1059): dye alpha starts at 1 */
+    for (size_t k = 0; k < nd; ++k) { s->dye[4 * k + 3] = 1.0f; s->dye2[4 * k + 3] = 1.0f; }
+    return s;
+}
+
+void oracle_sim_destroy(oracle_sim* s) {
+    if (!s) return;
+    free(s->v); free(s->v2); free(s->dye); free(s->dye2);
+    free(s->p); free(s->p2); free(s->div); free(s->curl_f);
+    free(s);
+}
+
+#define SWAP(a, b) do { float* t_ = (a); (a) = (b); (b) = t_; } while (0)
+#define ROUND(ptr, n) do { if (s->half_storage) oracle_round_half((ptr), (n)); } while (0)
+
+/* step(dt), S:1231-1294, pass by pass in the reference's order. */
+void oracle_sim_step(oracle_sim* s, float dt) {
+    const int W = s->W, H = s->H;
+    const size_t n = (size_t)W * H;
+    oracle_curl(s->v, s->curl_f, W, H);                                   /* S:1234-1237 */
+    ROUND(s->curl_f, n);
+    oracle_vorticity(s->v, s->curl_f, s->v2, W, H, s->curl, dt);          /* S:1239-1246 */
+    ROUND(s->v2, 2 * n); SWAP(s->v, s->v2);
+    oracle_divergence(s->v, s->div, W, H);                                /* S:1248-1251 */
+    ROUND(s->div, n);
+    oracle_clear(s->p, s->p2, n, s->pressure);                            /* S:1253-1257 */
+    ROUND(s->p2, n); SWAP(s->p, s->p2);
+    for (int k = 0; k < s->pressure_iterations; ++k) {                    /* S:1259-1266 */
+        oracle_jacobi(s->p, s->div, s->p2, W, H);
+        ROUND(s->p2, n); SWAP(s->p, s->p2);
+    }
+    oracle_gradient_subtract(s->p, s->v, s->v2, W, H);                    /* S:1268-1273 */
+    ROUND(s->v2, 2 * n); SWAP(s->v, s->v2);
+    oracle_advect(s->v, W, H, s->v, s->v2, W, H, 2, dt, s->velocity_dissipation); /* S:1275-1285 */
+    ROUND(s->v2, 2 * n); SWAP(s->v, s->v2);
+    oracle_advect(s->v, W, H, s->dye, s->dye2, s->Wd, s->Hd, 4, dt,
+                  s->density_dissipation);                                /* S:1287-1293 */
+    ROUND(s->dye2, 4 * (size_t)s->Wd * s->Hd); SWAP(s->dye, s->dye2);
+}
+
+/* splat(x,y,dx,dy,color), S:1441-1455, radius = correctRadius(SPLAT_RADIUS/100), S:1457-1462 */
+void oracle_sim_splat(oracle_sim* s, float x, float y, float dx, float dy, float r, float g,
+                      float b) {
+    /* JS evaluates correctRadius() in double and gl.uniform1f narrows it to fp32 */
+    double rad = (double)s->splat_radius / 100.0;
+    if (s->aspect > 1.0f) rad *= (double)s->aspect;
+    const float radius = (float)rad;
+    const float cv[3] = {dx, dy, 0.0f};
+    oracle_splat(s->v, s->v2, s->W, s->H, 2, s->aspect, x, y, cv, radius);
+    ROUND(s->v2, 2 * (size_t)s->W * s->H); SWAP(s->v, s->v2);
+    const float cd[3] = {r, g, b};
+    oracle_splat(s->dye, s->dye2, s->Wd, s->Hd, 4, s->aspect, x, y, cd, radius);
+    ROUND(s->dye2, 4 * (size_t)s->Wd * s->Hd); SWAP(s->dye, s->dye2);
+}

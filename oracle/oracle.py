@@ -1,0 +1,249 @@
+"""ctypes binding of the CPU oracle (oracle/libfluid_oracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  Nothing under webgl_fluid_simulation_b200/ imports it.
+
+Parity status: UNPINNED BY THE REFERENCE (it has no tests or fixtures and cannot run here);
+pinned against known-answer tests and against tests/golden/*.npz, which oracle/glsl_exec.py
+produced by executing the reference's own GLSL source text (see that file).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libfluid_oracle.so")
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "fluid_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _SO
+
+
+_lib = None
+_f = C.POINTER(C.c_float)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        L = C.CDLL(_SO)
+        i, f, sz = C.c_int, C.c_float, C.c_size_t
+        L.oracle_curl.argtypes = [_f, _f, i, i]
+        L.oracle_vorticity.argtypes = [_f, _f, _f, i, i, f, f]
+        L.oracle_divergence.argtypes = [_f, _f, i, i]
+        L.oracle_clear.argtypes = [_f, _f, sz, f]
+        L.oracle_jacobi.argtypes = [_f, _f, _f, i, i]
+        L.oracle_jacobi_iters.argtypes = [_f, _f, _f, i, i, i]
+        L.oracle_gradient_subtract.argtypes = [_f, _f, _f, i, i]
+        L.oracle_advect.argtypes = [_f, i, i, _f, _f, i, i, i, f, f]
+        L.oracle_splat.argtypes = [_f, _f, i, i, i, f, f, f, _f, f]
+        L.oracle_resample.argtypes = [_f, i, i, _f, i, i, i]
+        L.oracle_round_half.argtypes = [_f, sz]
+        L.oracle_num_threads.restype = i
+        for fn in (L.oracle_curl, L.oracle_vorticity, L.oracle_divergence, L.oracle_clear,
+                   L.oracle_jacobi, L.oracle_jacobi_iters, L.oracle_gradient_subtract,
+                   L.oracle_advect, L.oracle_splat, L.oracle_resample, L.oracle_round_half):
+            fn.restype = None
+        _lib = L
+    return _lib
+
+
+def _p(a: np.ndarray):
+    assert a.dtype == np.float32 and a.flags.c_contiguous
+    return a.ctypes.data_as(_f)
+
+
+def _c(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def num_threads() -> int:
+    return int(lib().oracle_num_threads())
+
+
+# Array conventions: scalar fields are (H, W); velocity (H, W, 2); dye (Hd, Wd, 4); row 0 = bottom.
+
+def curl(v):
+    v = _c(v); H, W, _ = v.shape
+    out = np.empty((H, W), np.float32)
+    lib().oracle_curl(_p(v), _p(out), W, H)
+    return out
+
+
+def vorticity(v, curl_f, curl_k, dt):
+    v = _c(v); curl_f = _c(curl_f); H, W, _ = v.shape
+    out = np.empty_like(v)
+    lib().oracle_vorticity(_p(v), _p(curl_f), _p(out), W, H, curl_k, dt)
+    return out
+
+
+def divergence(v):
+    v = _c(v); H, W, _ = v.shape
+    out = np.empty((H, W), np.float32)
+    lib().oracle_divergence(_p(v), _p(out), W, H)
+    return out
+
+
+def clear(p, value):
+    p = _c(p)
+    out = np.empty_like(p)
+    lib().oracle_clear(_p(p), _p(out), p.size, value)
+    return out
+
+
+def jacobi(p, div, iters=1):
+    p = _c(p).copy(); div = _c(div); H, W = p.shape
+    tmp = np.empty_like(p)
+    lib().oracle_jacobi_iters(_p(p), _p(tmp), _p(div), W, H, int(iters))
+    return p
+
+
+def gradient_subtract(p, v):
+    p = _c(p); v = _c(v); H, W = p.shape
+    out = np.empty_like(v)
+    lib().oracle_gradient_subtract(_p(p), _p(v), _p(out), W, H)
+    return out
+
+
+def advect(vel, src, dt, dissipation):
+    vel = _c(vel); src = _c(src)
+    H, W, _ = vel.shape
+    Hs, Ws, Cc = src.shape
+    out = np.empty_like(src)
+    lib().oracle_advect(_p(vel), W, H, _p(src), _p(out), Ws, Hs, Cc, dt, dissipation)
+    return out
+
+
+def splat(base, aspect, x, y, color3, radius):
+    base = _c(base); Hh, Ww, Cc = base.shape
+    out = np.empty_like(base)
+    col = np.asarray(color3, np.float32)
+    lib().oracle_splat(_p(base), _p(out), Ww, Hh, Cc, aspect, x, y, _p(col), radius)
+    return out
+
+
+def resample(src, Wd, Hd):
+    src = _c(src); Hs, Ws, Cc = src.shape
+    out = np.empty((Hd, Wd, Cc), np.float32)
+    lib().oracle_resample(_p(src), Ws, Hs, _p(out), Wd, Hd, Cc)
+    return out
+
+
+def round_half(a):
+    a = _c(a).copy()
+    lib().oracle_round_half(_p(a), a.size)
+    return a
+
+
+def correct_radius(splat_radius: float, aspect: float) -> np.float32:
+    """correctRadius(config.SPLAT_RADIUS / 100.0), S:1447 + S:1457-1462 (double math, fp32 uniform)."""
+    r = float(np.float32(splat_radius)) / 100.0
+    if aspect > 1:
+        r *= float(np.float32(aspect))
+    return np.float32(r)
+
+
+class OracleSim:
+    """The reference's global simulation state + step()/splat(), on the CPU (S:950-954, S:1231-1294,
+    S:1441-1455).  Orchestrated here in Python over the per-pass C functions so tests can peek at
+    every intermediate field; the C oracle_sim_* twin (used for CPU timing) is checked against it."""
+
+    def __init__(self, W, H, Wd, Hd, half_storage=False, **cfg):
+        self.W, self.H, self.Wd, self.Hd = W, H, Wd, Hd
+        self.DENSITY_DISSIPATION = 1.0
+        self.VELOCITY_DISSIPATION = 0.2
+        self.PRESSURE = 0.8
+        self.PRESSURE_ITERATIONS = 20
+        self.CURL = 30.0
+        self.SPLAT_RADIUS = 0.25
+        self.aspect = W / H
+        self.half_storage = half_storage
+        for k, v in cfg.items():
+            assert hasattr(self, k), k
+            setattr(self, k, v)
+        self.velocity = np.zeros((H, W, 2), np.float32)
+        self.dye = np.zeros((Hd, Wd, 4), np.float32)
+        self.dye[..., 3] = 1.0  # clearColor (0,0,0,1): S:136, S:1059
+        self.pressure = np.zeros((H, W), np.float32)
+        self.divergence = np.zeros((H, W), np.float32)
+        self.curl = np.zeros((H, W), np.float32)
+
+    def _st(self, a):
+        return round_half(a) if self.half_storage else a
+
+    def step(self, dt):
+        dt = float(np.float32(dt))
+        self.curl = self._st(curl(self.velocity))
+        self.velocity = self._st(vorticity(self.velocity, self.curl, self.CURL, dt))
+        self.divergence = self._st(divergence(self.velocity))
+        self.pressure = self._st(clear(self.pressure, self.PRESSURE))
+        if self.half_storage:
+            for _ in range(self.PRESSURE_ITERATIONS):
+                self.pressure = self._st(jacobi(self.pressure, self.divergence, 1))
+        else:
+            self.pressure = jacobi(self.pressure, self.divergence, self.PRESSURE_ITERATIONS)
+        self.velocity = self._st(gradient_subtract(self.pressure, self.velocity))
+        self.velocity = self._st(advect(self.velocity, self.velocity, dt, self.VELOCITY_DISSIPATION))
+        self.dye = self._st(advect(self.velocity, self.dye, dt, self.DENSITY_DISSIPATION))
+
+    def splat(self, x, y, dx, dy, r, g, b):
+        radius = correct_radius(self.SPLAT_RADIUS, self.aspect)
+        self.velocity = self._st(splat(self.velocity, self.aspect, x, y, (dx, dy, 0.0), radius))
+        self.dye = self._st(splat(self.dye, self.aspect, x, y, (r, g, b), radius))
+
+
+class OracleSimC:
+    """Thin handle over the C oracle_sim_* API (whole step in C; used for CPU timing)."""
+
+    class _S(C.Structure):
+        _fields_ = [("W", C.c_int), ("H", C.c_int), ("Wd", C.c_int), ("Hd", C.c_int),
+                    ("density_dissipation", C.c_float), ("velocity_dissipation", C.c_float),
+                    ("pressure", C.c_float), ("curl", C.c_float), ("splat_radius", C.c_float),
+                    ("aspect", C.c_float), ("pressure_iterations", C.c_int),
+                    ("half_storage", C.c_int),
+                    ("v", _f), ("v2", _f), ("dye", _f), ("dye2", _f), ("p", _f), ("p2", _f),
+                    ("div", _f), ("curl_f", _f)]
+
+    def __init__(self, W, H, Wd, Hd):
+        L = lib()
+        L.oracle_sim_create.restype = C.POINTER(self._S)
+        L.oracle_sim_create.argtypes = [C.c_int] * 4
+        L.oracle_sim_destroy.argtypes = [C.POINTER(self._S)]
+        L.oracle_sim_step.argtypes = [C.POINTER(self._S), C.c_float]
+        L.oracle_sim_splat.argtypes = [C.POINTER(self._S)] + [C.c_float] * 7
+        self._L = L
+        self.s = L.oracle_sim_create(W, H, Wd, Hd)
+
+    def step(self, dt):
+        self._L.oracle_sim_step(self.s, dt)
+
+    def splat(self, x, y, dx, dy, r, g, b):
+        self._L.oracle_sim_splat(self.s, x, y, dx, dy, r, g, b)
+
+    def field(self, name):
+        s = self.s.contents
+        shp = {"velocity": (s.H, s.W, 2), "dye": (s.Hd, s.Wd, 4), "pressure": (s.H, s.W),
+               "divergence": (s.H, s.W), "curl": (s.H, s.W)}[name]
+        ptr = {"velocity": s.v, "dye": s.dye, "pressure": s.p, "divergence": s.div,
+               "curl": s.curl_f}[name]
+        return np.ctypeslib.as_array(ptr, shape=(int(np.prod(shp)),)).reshape(shp).copy()
+
+    def close(self):
+        if self.s:
+            self._L.oracle_sim_destroy(self.s)
+            self.s = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

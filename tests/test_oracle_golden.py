@@ -1,0 +1,98 @@
+"""The CPU oracle against the golden vectors cut by executing the reference's GLSL text
+(tests/golden/make_golden.py -> oracle/glsl_exec.py).  Runs without a GPU."""
+import numpy as np
+import pytest
+
+from conftest import bits_equal, golden, max_rel
+
+PASS_FILES = ["pass_32x32_64x64", "pass_24x16_40x28", "pass_64x32_128x64", "pass_16x16_16x16"]
+# exp() is implementation-defined in GLSL: numpy's and glibc's expf differ in the last place
+SPLAT_TOL = 5e-7
+# for non-power-of-two grids the rasteriser's interpolated vUv and (i+.5)/W differ by an ulp,
+# which moves the bilinear taps' weights: value-level agreement only
+NONPOW2_ADVECT_TOL = 2e-5
+
+
+def _pow2(g):
+    return all(int(g[k]) & (int(g[k]) - 1) == 0 for k in ("W", "H", "Wd", "Hd"))
+
+
+@pytest.mark.parametrize("name", PASS_FILES)
+def test_passes_match_reference_shaders(oracle, name):
+    g = golden(name); O = oracle
+    dt = float(g["dt"]); v = g["in_velocity"]; p = g["in_pressure"]; dye = g["in_dye"]
+    W, H = int(g["W"]), int(g["H"])
+    c = O.curl(v); assert bits_equal(c, g["curl"])
+    v2 = O.vorticity(v, c, 30.0, dt); assert bits_equal(v2, g["vorticity"])
+    d = O.divergence(v2); assert bits_equal(d, g["divergence"])
+    p1 = O.clear(p, 0.8); assert bits_equal(p1, g["clear"])
+    p2 = O.jacobi(p1, d, 1); assert bits_equal(p2, g["jacobi1"])
+    p3 = O.jacobi(p2, d, 12); assert bits_equal(p3, g["jacobi13"])
+    v3 = O.gradient_subtract(p3, v2); assert bits_equal(v3, g["gradient"])
+    v4 = O.advect(v3, v3, dt, 0.2)
+    d2 = O.advect(g["advect_velocity"], dye, dt, 1.0)
+    if _pow2(g):
+        assert bits_equal(v4, g["advect_velocity"]) and bits_equal(d2, g["advect_dye"])
+    else:
+        assert max_rel(v4, g["advect_velocity"]) < NONPOW2_ADVECT_TOL
+        assert max_rel(d2, g["advect_dye"]) < NONPOW2_ADVECT_TOL
+    sp = g["splat_args"]; rad = O.correct_radius(0.25, W / H)
+    sv = O.splat(g["advect_velocity"], W / H, sp[0], sp[1], (sp[2], sp[3], 0.0), rad)
+    sd = O.splat(g["advect_dye"], W / H, sp[0], sp[1], tuple(sp[4:]), rad)
+    assert max_rel(sv, g["splat_velocity"]) < SPLAT_TOL
+    assert max_rel(sd, g["splat_dye"]) < SPLAT_TOL
+    assert np.all(sd[..., 3] == 1.0)       # splat forces alpha to 1 (S:742)
+
+
+def _run_scenario(O, g, sim_cls):
+    cfg = dict(zip([str(k) for k in g["config_keys"]], g["config_vals"]))
+    s = sim_cls(int(g["W"]), int(g["H"]), int(g["Wd"]), int(g["Hd"]))
+    s.CURL = float(cfg["CURL"]); s.PRESSURE_ITERATIONS = int(cfg["PRESSURE_ITERATIONS"])
+    for a in g["splats"]:
+        s.splat(*[float(x) for x in a])
+    return s
+
+
+@pytest.mark.parametrize("name,tol", [("step_curl30_32", 1e-5), ("step_curl30_48x32", 5e-5),  # 48 is not a power of two: vUv rounding
+                                      ("step_curl0_32", 2e-5)])
+def test_full_step_matches_reference_orchestration(oracle, name, tol):
+    """P2 / P3 of SURVEY §8c: short horizon with CURL=30, 20 steps with CURL=0."""
+    g = golden(name); O = oracle
+    s = _run_scenario(O, g, O.OracleSim)
+    assert max_rel(s.velocity, g["init_velocity"]) < SPLAT_TOL
+    assert max_rel(s.dye, g["init_dye"]) < SPLAT_TOL
+    steps = int(g["steps"])
+    for k in range(1, steps + 1):
+        s.step(float(g["dt"]))
+        if k in (1, 2, steps):
+            for n in ("velocity", "dye", "pressure", "divergence", "curl"):
+                assert max_rel(getattr(s, n), g[f"s{k}_{n}"]) < tol, (k, n)
+
+
+def test_c_step_equals_python_orchestration(oracle):
+    """oracle_sim_step (C, used for CPU timing) == the per-pass Python orchestration, bitwise."""
+    O = oracle; g = golden("step_curl30_32")
+    a = _run_scenario(O, g, O.OracleSim)
+    b = O.OracleSimC(32, 32, 64, 64)
+    for sp in g["splats"]:
+        b.splat(*[float(x) for x in sp])
+    for _ in range(3):
+        a.step(float(g["dt"])); b.step(float(g["dt"]))
+    for n in ("velocity", "dye", "pressure", "divergence", "curl"):
+        assert bits_equal(getattr(a, n), b.field(n)), n
+    b.close()
+
+
+def test_p4_report_distance_to_desktop_webgl(oracle, capsys):
+    """REPORT ONLY (never gates): distance from the fp32 oracle to the reference as a desktop
+    browser runs it (LINEAR samplers, half-float textures).  Bounds are loose sanity rails."""
+    O = oracle
+    for name, bound in (("p4_linear_fp32_32", 1e-4), ("p4_linear_half_32", 5e-2)):
+        g = golden(name)
+        s = _run_scenario(O, g, O.OracleSim)
+        s.step(float(g["dt"]))
+        e = {n: max_rel(getattr(s, n), g[f"s1_{n}"]) for n in ("velocity", "dye", "pressure")}
+        with capsys.disabled():
+            print(f"\n[P4] {name}: 1-step max-rel vs fp32 oracle: " +
+                  ", ".join(f"{k}={v:.2e}" for k, v in e.items()))
+        assert max(e.values()) < bound
