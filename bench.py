@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py — Jacobi pressure-solve throughput (BASELINE.json metric) on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" is one pass of the metric's hot path over one batch of synthetic input: the pressure
+solve of step() — clear (p <- PRESSURE*p, S:1253-1257) + PRESSURE_ITERATIONS Jacobi sweeps
+(S:1259-1266) — on BASELINE.json configs[2]: 4096x4096 fp32, 50 iterations, fields resident in HBM.
+`value` = W*H*iters*steps / device time (CUDA events on the library's own stream).
+`e2e`   = the same solve through the C-ABI call with HOST buffers (fluid_pressure_solve_host:
+          H2D divergence + pressure from pinned memory, solve, D2H pressure, all inside the call).
+`roofline` is for the dominant kernel (jacobi_tb_kernel) on ALGORITHMIC bytes (12 B / update, SURVEY
+§8d); temporal blocking moves far fewer DRAM bytes, so frac > 1 is expected and explained by
+`blocked_launches`, `compulsory_frac` and `traffic`; `roofline_naive` is the one-sweep-per-launch
+kernel measured the same way (<= 1 by construction).
+`--impl reference`: the reference cannot run here (browser + WebGL), so the reference
+arm is the CPU restatement of script.js (oracle/, kind "port") on all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "jacobi_cell_updates_per_sec"
+UNIT = "updates/s"
+W = H = 4096
+ITERS = 50
+ALGO_BYTES_PER_UPDATE = 12  # read p 4 + read div 4 + write p 4
+
+
+def peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Polls NVML for SM clock + throttle reasons while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self._stop = [], set(), threading.Event()
+        self.max_mhz = None
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            self.nv, self.h = nv, nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        nv = self.nv
+        names = {}
+        for n in dir(nv):
+            if n.startswith("nvmlClocksEventReason") or n.startswith("nvmlClocksThrottleReason"):
+                v = getattr(nv, n)
+                if isinstance(v, int) and v and (v & (v - 1)) == 0:
+                    names.setdefault(v, n.replace("nvmlClocksEventReason", "").replace("nvmlClocksThrottleReason", ""))
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit and nm not in ("None", "GpuIdle", "ApplicationsClocksSetting"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def __enter__(self):
+        if self.nv:
+            self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self.nv:
+            self.t.join(timeout=1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unsampled"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def synth_inputs(seed=42):
+    """SURVEY §8d isolated-Jacobi inputs: div ~ U(-1,1) seed 42; p ~ N(0,1) so the decay pass has work."""
+    rng = np.random.default_rng(seed)
+    d = rng.uniform(-1, 1, (H, W)).astype(np.float32)
+    p = rng.standard_normal((H, W)).astype(np.float32)
+    return p, d
+
+
+def cpu_port_rate(budget_s=10.0, cap=ITERS):
+    """CPU restatement of the pressure loop (oracle/, OpenMP, all host cores) on a bounded sample."""
+    from oracle import oracle as O
+    p, d = synth_inputs()
+    O.jacobi(p, d, 1)                                   # warm-up, page in
+    t0 = time.perf_counter(); O.jacobi(p, d, 2); t1 = time.perf_counter()
+    per = (t1 - t0) / 2
+    n = int(max(2, min(cap, budget_s / max(per, 1e-6))))
+    t0 = time.perf_counter(); O.jacobi(p, d, n); dt = time.perf_counter() - t0
+    return W * H * n / dt, O.num_threads(), f"{n} Jacobi sweeps of {W}x{H} fp32 (of the {ITERS}-sweep solve), {dt:.1f} s"
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    p, d = synth_inputs()
+    sweeps = 3                                           # bounded sample per step
+    for _ in range(max(args.warmup, 1)):
+        O.jacobi(p, d, 1)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.jacobi(p, d, sweeps)
+    dt = time.perf_counter() - t0
+    val = W * H * sweeps * args.steps / dt
+    sample = f"each step = {sweeps} Jacobi sweeps of {W}x{H} fp32 out of the {ITERS}-sweep solve"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"pressure solve {W}x{W} fp32, {ITERS} Jacobi iterations (BASELINE configs[2])",
+                   "note": "reference = CPU restatement of script.js (oracle/, OpenMP); the WebGL "
+                           "reference cannot run in this image (no browser / GL / node)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": O.num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def time_steps(sim, fn, steps):
+    sim.mark(0)
+    for _ in range(steps):
+        fn()
+    sim.mark(1)
+    return sim.elapsed_ms()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--jacobi-block", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import webgl_fluid_simulation_b200 as pkg
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the library has no CPU path")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    p0, d0 = synth_inputs()
+    cfg = {"SIM_RESOLUTION": W, "DYE_RESOLUTION": 64, "PRESSURE_ITERATIONS": ITERS}
+    sim = pkg.FluidSimulation(cfg, 1024, 1024, device=local, jacobi_block=args.jacobi_block)
+    sim.writeField("pressure", p0); sim.writeField("divergence", d0)
+    solve = lambda: sim.pass_("pressure_solve")
+
+    def barrier():
+        sim.sync(); torch.cuda.synchronize()
+        if dist: dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        solve()
+    barrier()
+    with ClockSampler(local) as clk:
+        ms = time_steps(sim, solve, args.steps)
+        sim.sync()
+        # keep the device loaded until NVML has a few samples even if the timed region is short
+        t_end = time.time() + 0.25
+        while len(clk.samples) < 5 and time.time() < t_end:
+            solve(); sim.sync()
+    barrier()
+    # exact launch count of the timed region: launches per solve x steps
+    l1 = sim.launch_count(); solve(); sim.sync(); per_step_launches = sim.launch_count() - l1
+    gpu_launches = per_step_launches * args.steps
+    if dist:
+        t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+    value = W * H * ITERS * args.steps * world / (ms * 1e-3)     # replicas until the slab path lands
+
+    peak, peak_src = peak_hbm()
+    achieved = ALGO_BYTES_PER_UPDATE * W * H * ITERS * args.steps / (ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "jacobi_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {
+        "kernel": "jacobi_tb_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+        "algorithmic_bytes_per_update": ALGO_BYTES_PER_UPDATE, "blocked_launches_per_step": per_step_launches,
+        "avg_launch_ms": ms / (args.steps * per_step_launches),
+        "algorithmic_bytes_per_launch": ALGO_BYTES_PER_UPDATE * W * H * ITERS / per_step_launches,
+        "compulsory_frac": (ALGO_BYTES_PER_UPDATE * W * H * per_step_launches * args.steps / (ms * 1e-3) / 1e9) / peak,
+        "note": "temporal blocking runs several sweeps per launch out of registers, so the "
+                "12 B/update algorithmic figure exceeds what DRAM actually moves; frac > 1 is "
+                "expected; compulsory_frac counts 12 B/cell once per launch",
+    }
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"pressure solve {W}x{W} fp32, {ITERS} Jacobi iterations (BASELINE configs[2])",
+                   "l2": "working set 192 MiB (p x2 + div) > 126 MB L2; no explicit flush",
+                   "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (row-slab path: see DESIGN.md)"},
+        "clocks": clk.summary(), "gpu_launches": gpu_launches, "roofline": roofline,
+    }
+
+    if rank == 0:
+        # ---- naive (one sweep per launch) kernel, same inputs, same timing method ----------------
+        nsim = pkg.FluidSimulation(cfg, 1024, 1024, device=local, flags=pkg.FLAG_NAIVE_JACOBI, jacobi_block=1)
+        nsim.writeField("pressure", p0); nsim.writeField("divergence", d0)
+        nsolve = lambda: nsim.pass_("pressure_solve")
+        for _ in range(3): nsolve()
+        nsim.sync()
+        nsteps = max(3, min(args.steps, 20))
+        nms = time_steps(nsim, nsolve, nsteps); nsim.sync()
+        nach = ALGO_BYTES_PER_UPDATE * W * H * ITERS * nsteps / (nms * 1e-3) / 1e9
+        out["roofline_naive"] = {"kernel": "jacobi_sweep_kernel", "bound": "hbm", "achieved": nach, "peak": peak,
+                                 "unit": "GB/s", "frac": nach / peak, "ms_per_step": nms / nsteps,
+                                 "updates_per_s": W * H * ITERS * nsteps / (nms * 1e-3)}
+        nsim.close()
+
+        # ---- e2e: host buffers through the C ABI ------------------------------------------------------
+        ph = torch.empty((H, W), dtype=torch.float32).pin_memory()
+        dh = torch.empty((H, W), dtype=torch.float32).pin_memory()
+        ph.numpy()[...] = p0; dh.numpy()[...] = d0
+        pn, dn = ph.numpy(), dh.numpy()
+        e_steps = max(3, min(args.steps, 10))
+        for _ in range(2):
+            sim.pressure_solve_host(dn, pn, ITERS)
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            sim.pressure_solve_host(dn, pn, ITERS)
+        e_dt = time.perf_counter() - t0
+        out["e2e"] = {"value": W * H * ITERS * e_steps * world / e_dt, "unit": UNIT,
+                      "h2d_bytes_per_step": 2 * W * H * 4, "d2h_bytes_per_step": W * H * 4,
+                      "ms_per_step": 1e3 * e_dt / e_steps, "steps": e_steps,
+                      "api": "fluid_pressure_solve_host (pinned host buffers; H2D div+p, solve, D2H p)"}
+
+        # ---- whole step() on configs[1] and configs[2], for context ---------------------------------
+        ctx = {}
+        for name, c in (("1024x1024 sim / 2048x2048 dye, 30 iters", {"SIM_RESOLUTION": 1024, "DYE_RESOLUTION": 2048, "PRESSURE_ITERATIONS": 30}),
+                        ("4096x4096 sim / 4096x4096 dye, 50 iters", {"SIM_RESOLUTION": 4096, "DYE_RESOLUTION": 4096, "PRESSURE_ITERATIONS": 50})):
+            s2 = pkg.FluidSimulation(c, 1024, 1024, device=local, flags=pkg.FLAG_NO_GRAPH, random=np.random.RandomState(1234).random_sample)
+            s2.multipleSplats(16)
+            for _ in range(3): s2.step(0.016666)
+            n2 = 10
+            m2 = time_steps(s2, lambda: s2.step(0.016666), n2); s2.sync()
+            tm = s2.timing()
+            ctx[name] = {"ms_per_step": m2 / n2, "passes_ms": {k: round(v, 4) for k, v in tm.items() if k.endswith("_ms")},
+                         "launches_per_step": tm["total_launches"]}
+            s2.close()
+        out["full_step"] = ctx
+
+        if not args.no_cpu:
+            v, cores, sample = cpu_port_rate()
+            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(out))
+    sim.close()
+    if dist:
+        dist.barrier(); dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,224 @@
+"""GPU parity: the CUDA library, called through the C ABI, against the CPU oracle and the golden
+vectors.  Bitwise for every pass whose arithmetic is IEEE-exact (all but splat's expf)."""
+import numpy as np
+import pytest
+
+from conftest import bits_equal, golden, max_rel
+
+pytestmark = pytest.mark.gpu
+DT = 0.016666
+SPLAT_TOL = 2e-6   # expf: CUDA <= 2 ulp, glibc < 1 ulp; on a term that is added to the base
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import webgl_fluid_simulation_b200 as p
+    return p
+
+
+def make(pkg, W, H, Wd, Hd, flags=0, jb=0, **cfg):
+    c = {"SIM_RESOLUTION": min(W, H), "DYE_RESOLUTION": min(Wd, Hd)}
+    c.update(cfg)
+    # canvas aspect chosen so getResolution yields exactly W x H / Wd x Hd
+    s = pkg.FluidSimulation(c, canvas_width=W, canvas_height=H, flags=flags, jacobi_block=jb)
+    assert s._dims("velocity")[:2] == (W, H), s._dims("velocity")
+    assert s._dims("dye")[:2] == (Wd, Hd), s._dims("dye")
+    return s
+
+
+def rand_fields(W, H, Wd, Hd, seed):
+    rng = np.random.default_rng(seed)
+    return ((rng.standard_normal((H, W, 2)) * 50).astype(np.float32),
+            rng.random((Hd, Wd, 4), dtype=np.float32),
+            rng.standard_normal((H, W)).astype(np.float32))
+
+
+SIZES = [(32, 32, 64, 64), (48, 32, 96, 64), (128, 128, 128, 128), (36, 20, 54, 30), (7, 5, 9, 6),
+         (256, 64, 512, 128), (1, 9, 3, 27), (9, 1, 27, 3)]
+
+
+@pytest.mark.parametrize("W,H,Wd,Hd", SIZES)
+def test_every_pass_bitwise_vs_oracle(pkg, oracle, W, H, Wd, Hd):
+    O = oracle
+    v, dye, p = rand_fields(W, H, Wd, Hd, W * 7 + H)
+    s = make(pkg, W, H, Wd, Hd)
+    s.writeField("velocity", v); s.writeField("dye", dye); s.writeField("pressure", p)
+    s.pass_("curl"); c = s.readField("curl"); assert bits_equal(c, O.curl(v))
+    s.pass_("vorticity", DT); v2 = s.readField("velocity")
+    assert bits_equal(v2, O.vorticity(v, c, 30.0, DT))
+    s.pass_("divergence"); d = s.readField("divergence"); assert bits_equal(d, O.divergence(v2))
+    s.pass_("clear_pressure"); p1 = s.readField("pressure"); assert bits_equal(p1, O.clear(p, 0.8))
+    s.pass_("jacobi", 1); p2 = s.readField("pressure"); assert bits_equal(p2, O.jacobi(p1, d, 1))
+    s.pass_("jacobi", 13); p3 = s.readField("pressure"); assert bits_equal(p3, O.jacobi(p2, d, 13))
+    s.pass_("gradient_subtract"); v3 = s.readField("velocity")
+    assert bits_equal(v3, O.gradient_subtract(p3, v2))
+    s.pass_("advect_velocity", DT); v4 = s.readField("velocity")
+    assert bits_equal(v4, O.advect(v3, v3, DT, 0.2))
+    s.pass_("advect_dye", DT); d2 = s.readField("dye")
+    assert bits_equal(d2, O.advect(v4, dye, DT, 1.0))
+    s.splat(0.3, 0.6, 123.0, -456.0, (0.5, 0.2, 0.9))
+    rad = O.correct_radius(0.25, W / H)
+    assert max_rel(s.readField("velocity"), O.splat(v4, W / H, 0.3, 0.6, (123.0, -456.0, 0), rad)) < SPLAT_TOL
+    sd = s.readField("dye")
+    assert max_rel(sd, O.splat(d2, W / H, 0.3, 0.6, (0.5, 0.2, 0.9), rad)) < SPLAT_TOL
+    assert np.all(sd[..., 3] == 1.0)
+    s.close()
+
+
+@pytest.mark.parametrize("name", ["pass_32x32_64x64", "pass_64x32_128x64", "pass_16x16_16x16"])
+def test_passes_vs_golden_reference_shader_outputs(pkg, name):
+    """Straight against the vectors cut by executing the reference's GLSL text (power-of-two grids:
+    bitwise for everything but splat)."""
+    g = golden(name)
+    W, H, Wd, Hd = (int(g[k]) for k in ("W", "H", "Wd", "Hd")); dt = float(g["dt"])
+    s = make(pkg, W, H, Wd, Hd, flags=pkg.FLAG_UNFUSED)
+    s.writeField("velocity", g["in_velocity"]); s.writeField("dye", g["in_dye"])
+    s.writeField("pressure", g["in_pressure"])
+    s.pass_("curl"); assert bits_equal(s.readField("curl"), g["curl"])
+    s.pass_("vorticity", dt); assert bits_equal(s.readField("velocity"), g["vorticity"])
+    s.pass_("divergence"); assert bits_equal(s.readField("divergence"), g["divergence"])
+    s.pass_("clear_pressure"); assert bits_equal(s.readField("pressure"), g["clear"])
+    s.pass_("jacobi", 1); assert bits_equal(s.readField("pressure"), g["jacobi1"])
+    s.pass_("jacobi", 12); assert bits_equal(s.readField("pressure"), g["jacobi13"])
+    s.pass_("gradient_subtract"); assert bits_equal(s.readField("velocity"), g["gradient"])
+    s.pass_("advect_velocity", dt); assert bits_equal(s.readField("velocity"), g["advect_velocity"])
+    s.pass_("advect_dye", dt); assert bits_equal(s.readField("dye"), g["advect_dye"])
+    sp = g["splat_args"]
+    s.splat(*[float(x) for x in sp[:4]], tuple(float(x) for x in sp[4:]))
+    assert max_rel(s.readField("velocity"), g["splat_velocity"]) < SPLAT_TOL
+    assert max_rel(s.readField("dye"), g["splat_dye"]) < SPLAT_TOL
+    s.close()
+
+
+@pytest.mark.parametrize("W,H", [(64, 40), (128, 128), (256, 96), (16, 2), (132, 77), (520, 33)])
+def test_fused_curl_vorticity_divergence_equals_three_passes(pkg, oracle, W, H):
+    O = oracle
+    v, _, _ = rand_fields(W, H, W, H, 11)
+    s = make(pkg, W, H, W, H)
+    s.writeField("velocity", v)
+    s.pass_("curl_vorticity_divergence", DT)
+    c = O.curl(v); v2 = O.vorticity(v, c, 30.0, DT)
+    assert bits_equal(s.readField("curl"), c)
+    assert bits_equal(s.readField("velocity"), v2)
+    assert bits_equal(s.readField("divergence"), O.divergence(v2))
+    s.close()
+
+
+@pytest.mark.parametrize("W,H,iters,jb", [(128, 64, 20, 8), (256, 200, 50, 8), (512, 96, 30, 10),
+                                          (16, 16, 9, 4), (1024, 1024, 50, 8), (132, 45, 17, 5),
+                                          (240, 300, 33, 7), (112, 2, 6, 3), (2048, 512, 40, 10)])
+def test_temporally_blocked_jacobi_bitwise_equals_naive_and_oracle(pkg, oracle, W, H, iters, jb):
+    """P5: K sweeps per launch == K launches of one sweep == the oracle, bit for bit; the fused
+    clear pass included (fluid_pass_pressure_solve == clear + iters x jacobi)."""
+    O = oracle
+    rng = np.random.default_rng(W + H + iters)
+    p = rng.standard_normal((H, W)).astype(np.float32)
+    d = rng.uniform(-1, 1, (H, W)).astype(np.float32)
+    outs = []
+    for flags, block in ((0, jb), (pkg.FLAG_NAIVE_JACOBI, 1)):
+        s = make(pkg, W, H, W, H, flags=flags, jb=block, PRESSURE_ITERATIONS=iters)
+        s.writeField("pressure", p); s.writeField("divergence", d)
+        s.pass_("pressure_solve")
+        outs.append(s.readField("pressure"))
+        s.close()
+    assert bits_equal(outs[0], outs[1])
+    if W * H <= 1 << 20:
+        assert bits_equal(outs[0], O.jacobi(O.clear(p, 0.8), d, iters))
+
+
+@pytest.mark.parametrize("name,tol", [("step_curl30_32", 1e-5), ("step_curl30_48x32", 5e-5),
+                                      ("step_curl0_32", 2e-5)])
+def test_full_step_vs_golden_scenarios(pkg, name, tol):
+    """P2/P3: whole step() through the public API against the executed-reference scenarios."""
+    g = golden(name)
+    cfg = dict(zip([str(k) for k in g["config_keys"]], [float(x) for x in g["config_vals"]]))
+    W, H, Wd, Hd = (int(g[k]) for k in ("W", "H", "Wd", "Hd"))
+    s = make(pkg, W, H, Wd, Hd, CURL=cfg["CURL"], PRESSURE_ITERATIONS=int(cfg["PRESSURE_ITERATIONS"]))
+    for a in g["splats"]:
+        s.splat(*[float(x) for x in a[:4]], tuple(float(x) for x in a[4:]))
+    steps = int(g["steps"])
+    for k in range(1, steps + 1):
+        s.step(float(g["dt"]))
+        if k in (1, 2, steps):
+            for n in ("velocity", "dye", "pressure", "divergence", "curl"):
+                assert max_rel(s.readField(n), g[f"s{k}_{n}"]) < tol, (k, n)
+    s.close()
+
+
+def test_full_step_bitwise_vs_oracle_when_no_splat_arithmetic(pkg, oracle):
+    """With identical start fields (written, not splatted) a whole step is bit-identical to the
+    oracle: fused kernels, temporal blocking and all."""
+    O = oracle
+    W = H = 256; Wd = Hd = 512
+    v, dye, p = rand_fields(W, H, Wd, Hd, 3)
+    s = make(pkg, W, H, Wd, Hd)
+    ref = O.OracleSim(W, H, Wd, Hd)
+    s.writeField("velocity", v); s.writeField("dye", dye); s.writeField("pressure", p)
+    ref.velocity, ref.dye, ref.pressure = v.copy(), dye.copy(), p.copy()
+    for _ in range(3):
+        s.step(DT); ref.step(DT)
+    for n in ("velocity", "dye", "pressure", "divergence", "curl"):
+        assert bits_equal(s.readField(n), getattr(ref, n)), n
+    s.close()
+
+
+def test_properties_at_full_size_4096(pkg):
+    """Size-independent properties at BASELINE config 3 (4096^2, 50 iterations), where the oracle
+    is too slow to run in a test: (1) blocked == naive bitwise; (2) linearity of the Jacobi map in
+    (p, div) for power-of-two scalings (exact in fp32); (3) constant p, zero div is a fixed point;
+    (4) the mirror symmetry of the clamp boundary: a left-right flipped input gives a flipped output."""
+    W = H = 4096; iters = 50
+    rng = np.random.default_rng(0)
+    p = rng.standard_normal((H, W)).astype(np.float32)
+    d = rng.uniform(-1, 1, (H, W)).astype(np.float32)
+
+    def solve(pp, dd, flags=0, jb=8):
+        s = make(pkg, W, H, 64, 64, flags=flags, jb=jb, PRESSURE_ITERATIONS=iters, PRESSURE=1.0)
+        s.writeField("pressure", pp); s.writeField("divergence", dd)
+        s.pass_("pressure_solve"); out = s.readField("pressure"); s.close()
+        return out
+    a = solve(p, d)
+    assert bits_equal(a, solve(p, d, flags=pkg.FLAG_NAIVE_JACOBI, jb=1))
+    assert bits_equal(solve(4 * p, 4 * d), 4 * a)
+    assert bits_equal(solve(np.full_like(p, 2.5), np.zeros_like(d)), np.full_like(p, 2.5))
+    assert bits_equal(solve(p[:, ::-1].copy(), d[:, ::-1].copy()), a[:, ::-1])
+
+
+def test_host_pressure_solve_matches_resident_path(pkg):
+    W = H = 512
+    rng = np.random.default_rng(1)
+    p = rng.standard_normal((H, W)).astype(np.float32)
+    d = rng.uniform(-1, 1, (H, W)).astype(np.float32)
+    s = make(pkg, W, H, 64, 64, PRESSURE_ITERATIONS=30)
+    s.writeField("pressure", p); s.writeField("divergence", d)
+    s.pass_("pressure_solve"); a = s.readField("pressure")
+    ph = p.copy()
+    s.pressure_solve_host(d, ph, 30)
+    assert bits_equal(a, ph)
+    s.close()
+
+
+def test_resize_carries_state_like_resizeDoubleFBO(pkg, oracle):
+    O = oracle
+    v, dye, p = rand_fields(32, 32, 64, 64, 9)
+    s = make(pkg, 32, 32, 64, 64)
+    s.writeField("velocity", v); s.writeField("dye", dye); s.writeField("pressure", p)
+    s.config["SIM_RESOLUTION"] = 48; s.config["DYE_RESOLUTION"] = 96
+    s.canvas = {"width": 512, "height": 512}
+    s.initFramebuffers()
+    assert bits_equal(s.readField("velocity"), O.resample(v, 48, 48))
+    assert bits_equal(s.readField("dye"), O.resample(dye, 96, 96))
+    assert not s.readField("pressure").any() and not s.readField("divergence").any()
+    s.close()
+
+
+def test_live_config_and_error_paths(pkg):
+    s = make(pkg, 64, 64, 64, 64)
+    s.config["PRESSURE_ITERATIONS"] = 3
+    s.step(DT)
+    with pytest.raises(pkg.FluidError):
+        s.writeField("velocity", np.zeros(5, np.float32))
+    with pytest.raises(pkg.FluidError):
+        s.set_param("CURL", 1.0) or s._check(s._L.fluid_set_param(s._h, 99, 0.0))
+    assert s.launch_count() > 0
+    s.close()

@@ -1,0 +1,674 @@
+// fluid.cu — libfluid_b200: the C ABI of include/fluid.h over the sm_100a kernels.
+//
+// Host-side structure mirrors the reference's globals (script.js S:950-954): five fields, three of
+// them DoubleFBO-style read/write pairs with swap() (S:1079-1106).  There is no CPU fallback:
+// every entry point either launches CUDA kernels on the handle's stream or fails.
+#include "../../include/fluid.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "jacobi.cuh"
+#include "passes.cuh"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Pair {              // createDoubleFBO, S:1079-1106
+    void* read = nullptr;
+    void* write = nullptr;
+    void swap() { std::swap(read, write); }
+};
+
+}  // namespace
+
+struct fluid {
+    fluid_config cfg{};
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t mark[2] = {nullptr, nullptr};
+    cudaEvent_t tev[8] = {};
+    Pair velocity, dye, pressure;    // float2 / float4 / float
+    float* divergence = nullptr;
+    float* curl = nullptr;
+    int* halo_flag = nullptr;        // device flag set by advection when a tap leaves the ghost zone
+    float* pin_a = nullptr;          // pinned staging for fluid_pressure_solve_host
+    float* pin_b = nullptr;
+    size_t pin_elems = 0;
+    uint64_t launches = 0;
+    fluid_timing timing{};
+    bool have_timing = false;
+    std::string err;
+    int jacobi_rows_override = 0;    // FLUID_JACOBI_ROWS env (tuning)
+
+    // single GPU: the slab is the whole grid
+    int row0 = 0, row1 = 0;          // owned sim rows
+    int drow0 = 0, drow1 = 0;        // owned dye rows
+};
+
+namespace {
+
+using namespace fk;
+
+int fail(fluid_t* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(h, FLUID_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                  \
+    } while (0)
+
+inline dim3 grid2d(int W, int rows, dim3 b) {
+    return dim3((W + b.x - 1) / b.x, (rows + b.y - 1) / b.y);
+}
+
+Grid sim_grid(const fluid_t* h) { return Grid{h->cfg.sim_w, h->cfg.sim_h, 0, h->row0, h->row1}; }
+Grid dye_grid(const fluid_t* h) { return Grid{h->cfg.dye_w, h->cfg.dye_h, 0, h->drow0, h->drow1}; }
+
+size_t sim_cells(const fluid_t* h) { return (size_t)h->cfg.sim_w * h->cfg.sim_h; }
+size_t dye_cells(const fluid_t* h) { return (size_t)h->cfg.dye_w * h->cfg.dye_h; }
+
+int check_launch(fluid_t* h, const char* what, int n = 1) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess)
+        return fail(h, FLUID_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+    h->launches += n;
+    return FLUID_OK;
+}
+
+// ---- Jacobi dispatch -----------------------------------------------------------------------------
+
+constexpr int KMAX = 10;
+
+template <int K, bool SCALE>
+int launch_tb(fluid_t* h, const JacobiArgs& a) {
+    using T = TB<K>;
+    static bool attr_set[64] = {};
+    auto kern = jacobi_tb_kernel<K, SCALE>;
+    if (!attr_set[h->device & 63]) {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM));
+        attr_set[h->device & 63] = true;
+    }
+    const int nxw = (a.W + T::VALID - 1) / T::VALID;
+    const int nch = (a.out_hi - a.out_lo + a.rows_per_chunk - 1) / a.rows_per_chunk;
+    const int nwarps = nxw * nch;
+    const int blocks = (nwarps + T::WARPS - 1) / T::WARPS;
+    kern<<<blocks, T::WARPS * 32, T::SMEM, h->stream>>>(a);
+    return check_launch(h, "jacobi_tb_kernel");
+}
+
+template <int K>
+int launch_tb_k(fluid_t* h, const JacobiArgs& a, bool scale) {
+    return scale ? launch_tb<K, true>(h, a) : launch_tb<K, false>(h, a);
+}
+
+// rows per warp stream: enough chunks that every SM holds `target` warps, single wave
+template <int K>
+int tb_rows(const fluid_t* h, int W, int rows) {
+    if (h->jacobi_rows_override > 0) return h->jacobi_rows_override;
+    using T = TB<K>;
+    const int nxw = (W + T::VALID - 1) / T::VALID;
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, jacobi_tb_kernel<K, false>, T::WARPS * 32,
+                                                  T::SMEM);
+    if (occ < 1) occ = 1;
+    const int resident_warps = h->sm_count * occ * T::WARPS;
+    int nch = std::max(1, resident_warps / nxw);
+    int r = (rows + nch - 1) / nch;
+    r = std::max(r, 4 * K);                 // keep the 2K warm-up rows a bounded fraction
+    return std::min(r, rows);
+}
+
+int launch_tb_dyn(fluid_t* h, int K, JacobiArgs a, bool scale) {
+    const int rows = a.out_hi - a.out_lo;
+    switch (K) {
+#define CASE(KK) case KK: a.rows_per_chunk = tb_rows<KK>(h, a.W, rows); return launch_tb_k<KK>(h, a, scale);
+        CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10)
+#undef CASE
+    }
+    return fail(h, FLUID_ERR_INVALID, "temporal block depth %d out of range", K);
+}
+
+bool tb_eligible(const fluid_t* h) {
+    return (h->cfg.sim_w % 4 == 0) && h->cfg.sim_w >= 16 && h->cfg.sim_h >= 2;
+}
+
+// `iters` sweeps reading pressure.read, result in pressure.read (swaps like S:1265).
+// scale_first: fold p <- PRESSURE*p (clear pass) into the first sweep's loads.
+int run_jacobi(fluid_t* h, int iters, bool scale_first, int* launches_out) {
+    int nl = 0;
+    const int W = h->cfg.sim_w, H = h->cfg.sim_h;
+    JacobiArgs a{};
+    a.div = h->divergence; a.W = W; a.H = H; a.row_off = 0; a.out_lo = h->row0; a.out_hi = h->row1;
+    a.scale = h->cfg.pressure;
+    int kb = h->cfg.jacobi_block > 0 ? h->cfg.jacobi_block : 8;
+    kb = std::min(kb, KMAX);
+    const bool naive = (h->cfg.flags & FLUID_FLAG_NAIVE_JACOBI) || kb == 1;
+    if (iters <= 0) {
+        if (scale_first) {   // clear pass alone
+            const size_t n = sim_cells(h);
+            scale_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(
+                (const float*)h->pressure.read, (float*)h->pressure.write, n, h->cfg.pressure);
+            int rc = check_launch(h, "scale_kernel"); if (rc) return rc;
+            h->pressure.swap(); ++nl;
+        }
+        if (launches_out) *launches_out = nl;
+        return FLUID_OK;
+    }
+    if (!tb_eligible(h)) {
+        dim3 b(64, 4);
+        for (int k = 0; k < iters; ++k) {
+            a.pin = (const float*)h->pressure.read; a.pout = (float*)h->pressure.write;
+            jacobi_scalar_kernel<<<grid2d(W, a.out_hi - a.out_lo, b), b, 0, h->stream>>>(
+                a, scale_first && k == 0);
+            int rc = check_launch(h, "jacobi_scalar_kernel"); if (rc) return rc;
+            h->pressure.swap(); ++nl;
+        }
+    } else if (naive) {
+        dim3 b(32, 8);
+        for (int k = 0; k < iters; ++k) {
+            a.pin = (const float*)h->pressure.read; a.pout = (float*)h->pressure.write;
+            dim3 g((W / 4 + b.x - 1) / b.x, (a.out_hi - a.out_lo + b.y - 1) / b.y);
+            if (scale_first && k == 0) jacobi_sweep_kernel<true><<<g, b, 0, h->stream>>>(a);
+            else jacobi_sweep_kernel<false><<<g, b, 0, h->stream>>>(a);
+            int rc = check_launch(h, "jacobi_sweep_kernel"); if (rc) return rc;
+            h->pressure.swap(); ++nl;
+        }
+    } else {
+        // balanced split of `iters` into ceil(iters/kb) launches of depth <= kb
+        const int n = (iters + kb - 1) / kb, base = iters / n, extra = iters % n;
+        for (int k = 0; k < n; ++k) {
+            const int K = base + (k < extra ? 1 : 0);
+            a.pin = (const float*)h->pressure.read; a.pout = (float*)h->pressure.write;
+            int rc = launch_tb_dyn(h, K, a, scale_first && k == 0); if (rc) return rc;
+            h->pressure.swap(); ++nl;
+        }
+    }
+    if (launches_out) *launches_out = nl;
+    return FLUID_OK;
+}
+
+int alloc_fields(fluid_t* h) {
+    const size_t n = sim_cells(h), nd = dye_cells(h);
+    CU(cudaMalloc(&h->velocity.read, n * sizeof(float2)));
+    CU(cudaMalloc(&h->velocity.write, n * sizeof(float2)));
+    CU(cudaMalloc(&h->dye.read, nd * sizeof(float4)));
+    CU(cudaMalloc(&h->dye.write, nd * sizeof(float4)));
+    CU(cudaMalloc(&h->pressure.read, n * sizeof(float)));
+    CU(cudaMalloc(&h->pressure.write, n * sizeof(float)));
+    CU(cudaMalloc((void**)&h->divergence, n * sizeof(float)));
+    CU(cudaMalloc((void**)&h->curl, n * sizeof(float)));
+    CU(cudaMemsetAsync(h->velocity.read, 0, n * sizeof(float2), h->stream));
+    CU(cudaMemsetAsync(h->velocity.write, 0, n * sizeof(float2), h->stream));
+    CU(cudaMemsetAsync(h->pressure.read, 0, n * sizeof(float), h->stream));
+    CU(cudaMemsetAsync(h->pressure.write, 0, n * sizeof(float), h->stream));
+    CU(cudaMemsetAsync(h->divergence, 0, n * sizeof(float), h->stream));
+    CU(cudaMemsetAsync(h->curl, 0, n * sizeof(float), h->stream));
+    fill_alpha_kernel<<<(unsigned)((nd + 255) / 256), 256, 0, h->stream>>>((float4*)h->dye.read, nd);
+    fill_alpha_kernel<<<(unsigned)((nd + 255) / 256), 256, 0, h->stream>>>((float4*)h->dye.write, nd);
+    return check_launch(h, "fill_alpha_kernel", 2);
+}
+
+void free_fields(fluid_t* h) {
+    cudaFree(h->velocity.read); cudaFree(h->velocity.write);
+    cudaFree(h->dye.read); cudaFree(h->dye.write);
+    cudaFree(h->pressure.read); cudaFree(h->pressure.write);
+    cudaFree(h->divergence); cudaFree(h->curl);
+    h->velocity = Pair{}; h->dye = Pair{}; h->pressure = Pair{};
+    h->divergence = h->curl = nullptr;
+}
+
+int field_info(const fluid_t* h, int field, void** ptr, int* w, int* rows, int* ch) {
+    switch (field) {
+        case FLUID_FIELD_VELOCITY: *ptr = h->velocity.read; *w = h->cfg.sim_w; *rows = h->row1 - h->row0; *ch = 2; return 0;
+        case FLUID_FIELD_DYE: *ptr = h->dye.read; *w = h->cfg.dye_w; *rows = h->drow1 - h->drow0; *ch = 4; return 0;
+        case FLUID_FIELD_PRESSURE: *ptr = h->pressure.read; *w = h->cfg.sim_w; *rows = h->row1 - h->row0; *ch = 1; return 0;
+        case FLUID_FIELD_DIVERGENCE: *ptr = h->divergence; *w = h->cfg.sim_w; *rows = h->row1 - h->row0; *ch = 1; return 0;
+        case FLUID_FIELD_CURL: *ptr = h->curl; *w = h->cfg.sim_w; *rows = h->row1 - h->row0; *ch = 1; return 0;
+    }
+    return -1;
+}
+
+int check_halo(fluid_t* h) { (void)h; return FLUID_OK; }  // single GPU: taps are always clamped in-grid
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int fluid_abi_version(void) { return FLUID_ABI_VERSION; }
+
+void fluid_config_default(fluid_config* c) {
+    memset(c, 0, sizeof *c);
+    c->sim_w = c->sim_h = 128;            // SIM_RESOLUTION  S:60
+    c->dye_w = c->dye_h = 1024;           // DYE_RESOLUTION  S:61
+    c->density_dissipation = 1.0f;        // S:63
+    c->velocity_dissipation = 0.2f;       // S:64
+    c->pressure = 0.8f;                   // S:65
+    c->pressure_iterations = 20;          // S:66
+    c->curl = 30.0f;                      // S:67
+    c->splat_radius = 0.25f;              // S:68
+    c->aspect = 1.0f;
+    c->device = -1;
+    c->flags = 0;
+    c->jacobi_block = 0;
+}
+
+// getResolution, S:1612-1624
+void fluid_get_resolution(int resolution, int canvas_w, int canvas_h, int* out_w, int* out_h) {
+    double aspect = (double)canvas_w / (double)canvas_h;
+    if (aspect < 1.0) aspect = 1.0 / aspect;
+    // Math.round: half away from zero for positive values == floor(x + 0.5)
+    const int mn = (int)(resolution + 0.5);
+    const int mx = (int)((double)resolution * aspect + 0.5);
+    if (canvas_w > canvas_h) { *out_w = mx; *out_h = mn; }
+    else { *out_w = mn; *out_h = mx; }
+}
+
+const char* fluid_last_error(fluid_t* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int fluid_create(const fluid_config* cfg, fluid_t** out) {
+    fluid_t* h = nullptr;
+    if (!cfg || !out) return fail(h, FLUID_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->sim_w < 1 || cfg->sim_h < 1 || cfg->dye_w < 1 || cfg->dye_h < 1)
+        return fail(h, FLUID_ERR_INVALID, "bad resolution %dx%d / %dx%d", cfg->sim_w, cfg->sim_h,
+                    cfg->dye_w, cfg->dye_h);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(h, FLUID_ERR_NO_DEVICE, "no CUDA device: libfluid_b200 has no CPU path");
+    }
+    int dev = cfg->device;
+    if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) dev = 0; }
+    if (dev >= ndev) return fail(h, FLUID_ERR_INVALID, "device %d of %d", dev, ndev);
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess || prop.major != 10)
+        return fail(h, FLUID_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only",
+                    dev, prop.major, prop.minor);
+    if (cudaSetDevice(dev) != cudaSuccess) return fail(h, FLUID_ERR_CUDA, "cudaSetDevice(%d)", dev);
+
+    h = new fluid();
+    h->cfg = *cfg;
+    h->device = dev;
+    h->sm_count = prop.multiProcessorCount;
+    if (!(h->cfg.aspect > 0.0f)) h->cfg.aspect = (float)((double)cfg->sim_w / (double)cfg->sim_h);
+    h->row0 = 0; h->row1 = cfg->sim_h; h->drow0 = 0; h->drow1 = cfg->dye_h;
+    if (const char* e = getenv("FLUID_JACOBI_ROWS")) h->jacobi_rows_override = atoi(e);
+    int rc = FLUID_OK;
+    auto body = [&]() -> int {
+        CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        for (auto& e : h->mark) CU(cudaEventCreate(&e));
+        for (auto& e : h->tev) CU(cudaEventCreate(&e));
+        CU(cudaMalloc((void**)&h->halo_flag, sizeof(int)));
+        CU(cudaMemsetAsync(h->halo_flag, 0, sizeof(int), h->stream));
+        int r = alloc_fields(h); if (r) return r;
+        CU(cudaStreamSynchronize(h->stream));
+        return FLUID_OK;
+    };
+    rc = body();
+    if (rc != FLUID_OK) { g_create_error = h->err; fluid_destroy(h); return rc; }
+    *out = h;
+    return FLUID_OK;
+}
+
+int fluid_nccl_unique_id(void* out_uid, size_t uid_bytes) {
+    (void)out_uid; (void)uid_bytes;
+    return fail(nullptr, FLUID_ERR_NCCL, "multi-GPU slabs are not built into this library yet");
+}
+
+int fluid_create_slab(const fluid_config* cfg, int rank, int world, const void* nccl_uid,
+                      size_t uid_bytes, fluid_t** out) {
+    (void)nccl_uid; (void)uid_bytes;
+    if (world == 1 && rank == 0) return fluid_create(cfg, out);
+    return fail(nullptr, FLUID_ERR_NCCL, "multi-GPU slabs are not built into this library yet");
+}
+
+void fluid_destroy(fluid_t* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    free_fields(h);
+    cudaFree(h->halo_flag);
+    if (h->pin_a) cudaFreeHost(h->pin_a);
+    if (h->pin_b) cudaFreeHost(h->pin_b);
+    for (auto& e : h->mark) if (e) cudaEventDestroy(e);
+    for (auto& e : h->tev) if (e) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int fluid_set_param(fluid_t* h, int key, float v) {
+    if (!h) return FLUID_ERR_INVALID;
+    switch (key) {
+        case FLUID_DENSITY_DISSIPATION: h->cfg.density_dissipation = v; break;
+        case FLUID_VELOCITY_DISSIPATION: h->cfg.velocity_dissipation = v; break;
+        case FLUID_PRESSURE: h->cfg.pressure = v; break;
+        case FLUID_PRESSURE_ITERATIONS: h->cfg.pressure_iterations = (int)(v + 0.5f); break;
+        case FLUID_CURL: h->cfg.curl = v; break;
+        case FLUID_SPLAT_RADIUS: h->cfg.splat_radius = v; break;
+        case FLUID_ASPECT: h->cfg.aspect = v; break;
+        case FLUID_JACOBI_BLOCK: h->cfg.jacobi_block = (int)(v + 0.5f); break;
+        default: return fail(h, FLUID_ERR_INVALID, "unknown param key %d", key);
+    }
+    return FLUID_OK;
+}
+
+int fluid_get_param(fluid_t* h, int key, float* v) {
+    if (!h || !v) return FLUID_ERR_INVALID;
+    switch (key) {
+        case FLUID_DENSITY_DISSIPATION: *v = h->cfg.density_dissipation; break;
+        case FLUID_VELOCITY_DISSIPATION: *v = h->cfg.velocity_dissipation; break;
+        case FLUID_PRESSURE: *v = h->cfg.pressure; break;
+        case FLUID_PRESSURE_ITERATIONS: *v = (float)h->cfg.pressure_iterations; break;
+        case FLUID_CURL: *v = h->cfg.curl; break;
+        case FLUID_SPLAT_RADIUS: *v = h->cfg.splat_radius; break;
+        case FLUID_ASPECT: *v = h->cfg.aspect; break;
+        case FLUID_JACOBI_BLOCK: *v = (float)h->cfg.jacobi_block; break;
+        default: return fail(h, FLUID_ERR_INVALID, "unknown param key %d", key);
+    }
+    return FLUID_OK;
+}
+
+// ---- passes ---------------------------------------------------------------------------------------
+
+int fluid_pass_curl(fluid_t* h) {
+    if (!h) return FLUID_ERR_INVALID;
+    dim3 b(64, 4); Grid g = sim_grid(h);
+    curl_kernel<<<grid2d(g.W, g.j_hi - g.j_lo, b), b, 0, h->stream>>>((const float2*)h->velocity.read,
+                                                                     h->curl, g);
+    return check_launch(h, "curl_kernel");
+}
+
+int fluid_pass_vorticity(fluid_t* h, float dt) {
+    if (!h) return FLUID_ERR_INVALID;
+    dim3 b(64, 4); Grid g = sim_grid(h);
+    vorticity_kernel<<<grid2d(g.W, g.j_hi - g.j_lo, b), b, 0, h->stream>>>(
+        (const float2*)h->velocity.read, h->curl, (float2*)h->velocity.write, g, h->cfg.curl, dt);
+    int rc = check_launch(h, "vorticity_kernel"); if (rc) return rc;
+    h->velocity.swap();                                   // S:1246
+    return FLUID_OK;
+}
+
+int fluid_pass_divergence(fluid_t* h) {
+    if (!h) return FLUID_ERR_INVALID;
+    dim3 b(64, 4); Grid g = sim_grid(h);
+    divergence_kernel<<<grid2d(g.W, g.j_hi - g.j_lo, b), b, 0, h->stream>>>(
+        (const float2*)h->velocity.read, h->divergence, g);
+    return check_launch(h, "divergence_kernel");
+}
+
+int fluid_pass_curl_vorticity_divergence(fluid_t* h, float dt) {
+    if (!h) return FLUID_ERR_INVALID;
+    Grid g = sim_grid(h);
+    dim3 b(64, 4);
+    dim3 grid((g.W + CVD_TX - 1) / CVD_TX, (g.j_hi - g.j_lo + CVD_TY - 1) / CVD_TY);
+    curl_vorticity_divergence_kernel<<<grid, b, 0, h->stream>>>(
+        (const float2*)h->velocity.read, h->curl, (float2*)h->velocity.write, h->divergence, g,
+        h->cfg.curl, dt);
+    int rc = check_launch(h, "curl_vorticity_divergence_kernel"); if (rc) return rc;
+    h->velocity.swap();
+    return FLUID_OK;
+}
+
+int fluid_pass_clear_pressure(fluid_t* h) {
+    if (!h) return FLUID_ERR_INVALID;
+    return run_jacobi(h, 0, true, nullptr);
+}
+
+int fluid_pass_jacobi(fluid_t* h, int iters) {
+    if (!h) return FLUID_ERR_INVALID;
+    if (iters < 0) return fail(h, FLUID_ERR_INVALID, "iters < 0");
+    return run_jacobi(h, iters, false, nullptr);
+}
+
+int fluid_pass_pressure_solve(fluid_t* h) {
+    if (!h) return FLUID_ERR_INVALID;
+    return run_jacobi(h, h->cfg.pressure_iterations, true, nullptr);
+}
+
+int fluid_pass_gradient_subtract(fluid_t* h) {
+    if (!h) return FLUID_ERR_INVALID;
+    dim3 b(64, 4); Grid g = sim_grid(h);
+    gradient_subtract_kernel<<<grid2d(g.W, g.j_hi - g.j_lo, b), b, 0, h->stream>>>(
+        (const float*)h->pressure.read, (const float2*)h->velocity.read, (float2*)h->velocity.write, g);
+    int rc = check_launch(h, "gradient_subtract_kernel"); if (rc) return rc;
+    h->velocity.swap();                                   // S:1273
+    return FLUID_OK;
+}
+
+int fluid_pass_advect_velocity(fluid_t* h, float dt) {
+    if (!h) return FLUID_ERR_INVALID;
+    dim3 b(64, 4);
+    AdvectArgs a{};
+    a.vel = sim_grid(h); a.src = sim_grid(h);
+    a.vel_lo = 0; a.vel_hi = h->cfg.sim_h; a.src_lo = 0; a.src_hi = h->cfg.sim_h;
+    a.dt = dt; a.dissipation = h->cfg.velocity_dissipation; a.halo_violation = h->halo_flag;
+    advect_velocity_kernel<<<grid2d(a.src.W, a.src.j_hi - a.src.j_lo, b), b, 0, h->stream>>>(
+        (const float2*)h->velocity.read, (float2*)h->velocity.write, a);
+    int rc = check_launch(h, "advect_velocity_kernel"); if (rc) return rc;
+    h->velocity.swap();                                   // S:1285
+    return FLUID_OK;
+}
+
+int fluid_pass_advect_dye(fluid_t* h, float dt) {
+    if (!h) return FLUID_ERR_INVALID;
+    dim3 b(64, 4);
+    AdvectArgs a{};
+    a.vel = sim_grid(h); a.src = dye_grid(h);
+    a.vel_lo = 0; a.vel_hi = h->cfg.sim_h; a.src_lo = 0; a.src_hi = h->cfg.dye_h;
+    a.dt = dt; a.dissipation = h->cfg.density_dissipation; a.halo_violation = h->halo_flag;
+    advect_dye_kernel<<<grid2d(a.src.W, a.src.j_hi - a.src.j_lo, b), b, 0, h->stream>>>(
+        (const float2*)h->velocity.read, (const float4*)h->dye.read, (float4*)h->dye.write, a);
+    int rc = check_launch(h, "advect_dye_kernel"); if (rc) return rc;
+    h->dye.swap();                                        // S:1293
+    return FLUID_OK;
+}
+
+// step(dt), S:1231-1294
+int fluid_step(fluid_t* h, float dt) {
+    if (!h) return FLUID_ERR_INVALID;
+    const uint64_t l0 = h->launches;
+    const bool timed = (h->cfg.flags & FLUID_FLAG_NO_GRAPH) != 0;
+    int rc;
+    int jl = 0;
+    if (timed) cudaEventRecord(h->tev[0], h->stream);
+    if (h->cfg.flags & FLUID_FLAG_UNFUSED) {
+        if ((rc = fluid_pass_curl(h))) return rc;
+        if ((rc = fluid_pass_vorticity(h, dt))) return rc;
+        if ((rc = fluid_pass_divergence(h))) return rc;
+    } else {
+        if ((rc = fluid_pass_curl_vorticity_divergence(h, dt))) return rc;
+    }
+    if (timed) cudaEventRecord(h->tev[1], h->stream);
+    if ((rc = run_jacobi(h, h->cfg.pressure_iterations, true, &jl))) return rc;
+    if (timed) cudaEventRecord(h->tev[2], h->stream);
+    if ((rc = fluid_pass_gradient_subtract(h))) return rc;
+    if (timed) cudaEventRecord(h->tev[3], h->stream);
+    if ((rc = fluid_pass_advect_velocity(h, dt))) return rc;
+    if (timed) cudaEventRecord(h->tev[4], h->stream);
+    if ((rc = fluid_pass_advect_dye(h, dt))) return rc;
+    if (timed) cudaEventRecord(h->tev[5], h->stream);
+    h->timing.jacobi_launches = jl;
+    h->timing.total_launches = (int)(h->launches - l0);
+    h->have_timing = timed;
+    return check_halo(h);
+}
+
+// splat(x,y,dx,dy,color), S:1441-1455
+int fluid_splat(fluid_t* h, float x, float y, float dx, float dy, float r, float g, float b) {
+    if (!h) return FLUID_ERR_INVALID;
+    // correctRadius(config.SPLAT_RADIUS / 100.0): JS double arithmetic, narrowed by gl.uniform1f
+    double rad = (double)h->cfg.splat_radius / 100.0;
+    if (h->cfg.aspect > 1.0f) rad *= (double)h->cfg.aspect;
+    const float radius = (float)rad;
+    dim3 bl(64, 4);
+    Grid gs = sim_grid(h), gd = dye_grid(h);
+    splat_velocity_kernel<<<grid2d(gs.W, gs.j_hi - gs.j_lo, bl), bl, 0, h->stream>>>(
+        (const float2*)h->velocity.read, (float2*)h->velocity.write, gs, h->cfg.aspect, x, y, dx, dy,
+        radius);
+    int rc = check_launch(h, "splat_velocity_kernel"); if (rc) return rc;
+    h->velocity.swap();                                   // S:1449
+    splat_dye_kernel<<<grid2d(gd.W, gd.j_hi - gd.j_lo, bl), bl, 0, h->stream>>>(
+        (const float4*)h->dye.read, (float4*)h->dye.write, gd, h->cfg.aspect, x, y, r, g, b, radius);
+    rc = check_launch(h, "splat_dye_kernel"); if (rc) return rc;
+    h->dye.swap();                                        // S:1454
+    return FLUID_OK;
+}
+
+// initFramebuffers() on a live simulation: S:982-1010 + resizeDoubleFBO S:1116-1126
+int fluid_resize(fluid_t* h, int sim_w, int sim_h, int dye_w, int dye_h) {
+    if (!h) return FLUID_ERR_INVALID;
+    if (sim_w < 1 || sim_h < 1 || dye_w < 1 || dye_h < 1) return fail(h, FLUID_ERR_INVALID, "bad size");
+    const int ow = h->cfg.sim_w, oh = h->cfg.sim_h, odw = h->cfg.dye_w, odh = h->cfg.dye_h;
+    dim3 b(64, 4);
+    const size_t n = (size_t)sim_w * sim_h, nd = (size_t)dye_w * dye_h;
+    if (dye_w != odw || dye_h != odh) {
+        float4 *nr = nullptr, *nw = nullptr;
+        CU(cudaMalloc((void**)&nr, nd * sizeof(float4)));
+        CU(cudaMalloc((void**)&nw, nd * sizeof(float4)));
+        resample_kernel<float4><<<grid2d(dye_w, dye_h, b), b, 0, h->stream>>>(
+            (const float4*)h->dye.read, odw, odh, nr, dye_w, dye_h);
+        fill_alpha_kernel<<<(unsigned)((nd + 255) / 256), 256, 0, h->stream>>>(nw, nd);
+        int rc = check_launch(h, "resample_kernel", 2); if (rc) return rc;
+        CU(cudaStreamSynchronize(h->stream));
+        cudaFree(h->dye.read); cudaFree(h->dye.write);
+        h->dye.read = nr; h->dye.write = nw;
+    }
+    if (sim_w != ow || sim_h != oh) {
+        float2 *nr = nullptr, *nw = nullptr;
+        CU(cudaMalloc((void**)&nr, n * sizeof(float2)));
+        CU(cudaMalloc((void**)&nw, n * sizeof(float2)));
+        resample_kernel<float2><<<grid2d(sim_w, sim_h, b), b, 0, h->stream>>>(
+            (const float2*)h->velocity.read, ow, oh, nr, sim_w, sim_h);
+        int rc = check_launch(h, "resample_kernel"); if (rc) return rc;
+        CU(cudaMemsetAsync(nw, 0, n * sizeof(float2), h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        cudaFree(h->velocity.read); cudaFree(h->velocity.write);
+        h->velocity.read = nr; h->velocity.write = nw;
+    }
+    // divergence, curl, pressure are always re-created (createFBO / createDoubleFBO, S:1004-1006)
+    cudaFree(h->pressure.read); cudaFree(h->pressure.write); cudaFree(h->divergence); cudaFree(h->curl);
+    h->pressure = Pair{}; h->divergence = h->curl = nullptr;
+    CU(cudaMalloc(&h->pressure.read, n * sizeof(float)));
+    CU(cudaMalloc(&h->pressure.write, n * sizeof(float)));
+    CU(cudaMalloc((void**)&h->divergence, n * sizeof(float)));
+    CU(cudaMalloc((void**)&h->curl, n * sizeof(float)));
+    CU(cudaMemsetAsync(h->pressure.read, 0, n * sizeof(float), h->stream));
+    CU(cudaMemsetAsync(h->pressure.write, 0, n * sizeof(float), h->stream));
+    CU(cudaMemsetAsync(h->divergence, 0, n * sizeof(float), h->stream));
+    CU(cudaMemsetAsync(h->curl, 0, n * sizeof(float), h->stream));
+    h->cfg.sim_w = sim_w; h->cfg.sim_h = sim_h; h->cfg.dye_w = dye_w; h->cfg.dye_h = dye_h;
+    h->row0 = 0; h->row1 = sim_h; h->drow0 = 0; h->drow1 = dye_h;
+    return FLUID_OK;
+}
+
+// ---- data in / out --------------------------------------------------------------------------------
+
+size_t fluid_field_elems(fluid_t* h, int field) {
+    void* p; int w, rows, ch;
+    if (!h || field_info(h, field, &p, &w, &rows, &ch)) return 0;
+    return (size_t)w * rows * ch;
+}
+
+int fluid_field_dims(fluid_t* h, int field, int* w, int* rows, int* ch, int* row0) {
+    void* p; int ww, rr, cc;
+    if (!h || field_info(h, field, &p, &ww, &rr, &cc)) return FLUID_ERR_INVALID;
+    if (w) *w = ww; if (rows) *rows = rr; if (ch) *ch = cc;
+    if (row0) *row0 = (field == FLUID_FIELD_DYE) ? h->drow0 : h->row0;
+    return FLUID_OK;
+}
+
+int fluid_read(fluid_t* h, int field, float* host, size_t n_floats) {
+    void* p; int w, rows, ch;
+    if (!h || !host || field_info(h, field, &p, &w, &rows, &ch)) return fail(h, FLUID_ERR_INVALID, "bad field %d", field);
+    const size_t n = (size_t)w * rows * ch;
+    if (n_floats != n) return fail(h, FLUID_ERR_INVALID, "field %d has %zu floats, caller passed %zu", field, n, n_floats);
+    CU(cudaMemcpyAsync(host, p, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return FLUID_OK;
+}
+
+int fluid_write(fluid_t* h, int field, const float* host, size_t n_floats) {
+    void* p; int w, rows, ch;
+    if (!h || !host || field_info(h, field, &p, &w, &rows, &ch)) return fail(h, FLUID_ERR_INVALID, "bad field %d", field);
+    const size_t n = (size_t)w * rows * ch;
+    if (n_floats != n) return fail(h, FLUID_ERR_INVALID, "field %d has %zu floats, caller passed %zu", field, n, n_floats);
+    CU(cudaMemcpyAsync(p, host, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return FLUID_OK;
+}
+
+int fluid_pressure_solve_host(fluid_t* h, const float* div_host, float* p_host, int iters) {
+    if (!h || !div_host || !p_host || iters < 0) return fail(h, FLUID_ERR_INVALID, "bad argument");
+    const size_t n = sim_cells(h);
+    // Host buffers may be pageable; pinned ones (cudaHostAlloc / cudaHostRegister by the caller)
+    // make the copies asynchronous DMA.  Either way all three copies are inside this call.
+    CU(cudaMemcpyAsync(h->divergence, div_host, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->pressure.read, p_host, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    int rc = run_jacobi(h, iters, true, nullptr); if (rc) return rc;
+    CU(cudaMemcpyAsync(p_host, h->pressure.read, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return FLUID_OK;
+}
+
+int fluid_sync(fluid_t* h) {
+    if (!h) return FLUID_ERR_INVALID;
+    CU(cudaStreamSynchronize(h->stream));
+    return check_halo(h);
+}
+
+int fluid_timing_last(fluid_t* h, fluid_timing* out) {
+    if (!h || !out) return FLUID_ERR_INVALID;
+    if (!h->have_timing) return fail(h, FLUID_ERR_INVALID, "per-pass timing needs FLUID_FLAG_NO_GRAPH");
+    CU(cudaStreamSynchronize(h->stream));
+    float ms[5];
+    for (int k = 0; k < 5; ++k) CU(cudaEventElapsedTime(&ms[k], h->tev[k], h->tev[k + 1]));
+    h->timing.curl_vort_div_ms = ms[0]; h->timing.jacobi_ms = ms[1]; h->timing.gradient_ms = ms[2];
+    h->timing.advect_velocity_ms = ms[3]; h->timing.advect_dye_ms = ms[4];
+    CU(cudaEventElapsedTime(&h->timing.total_ms, h->tev[0], h->tev[5]));
+    *out = h->timing;
+    return FLUID_OK;
+}
+
+int fluid_mark(fluid_t* h, int slot) {
+    if (!h || slot < 0 || slot > 1) return FLUID_ERR_INVALID;
+    CU(cudaEventRecord(h->mark[slot], h->stream));
+    return FLUID_OK;
+}
+
+int fluid_elapsed_ms(fluid_t* h, float* ms) {
+    if (!h || !ms) return FLUID_ERR_INVALID;
+    CU(cudaEventSynchronize(h->mark[1]));
+    CU(cudaEventElapsedTime(ms, h->mark[0], h->mark[1]));
+    return FLUID_OK;
+}
+
+uint64_t fluid_launch_count(fluid_t* h) { return h ? h->launches : 0; }
+
+void* fluid_device_ptr(fluid_t* h, int field) {
+    void* p; int w, rows, ch;
+    if (!h || field_info(h, field, &p, &w, &rows, &ch)) return nullptr;
+    return p;
+}
+
+}  // extern "C"
