@@ -19,8 +19,10 @@ def pkg():
 def make(pkg, W, H, Wd, Hd, flags=0, jb=0, **cfg):
     c = {"SIM_RESOLUTION": min(W, H), "DYE_RESOLUTION": min(Wd, Hd)}
     c.update(cfg)
-    # canvas aspect chosen so getResolution yields exactly W x H / Wd x Hd
-    s = pkg.FluidSimulation(c, canvas_width=W, canvas_height=H, flags=flags, jacobi_block=jb)
+    # canvas aspect = W/H like the reference; exact sizes are forced through the test hook because
+    # getResolution rounds (e.g. a 9x6 dye grid is not reachable from a 7:5 canvas)
+    s = pkg.FluidSimulation(c, canvas_width=W, canvas_height=H, flags=flags, jacobi_block=jb,
+                            sizes=(W, H, Wd, Hd))
     assert s._dims("velocity")[:2] == (W, H), s._dims("velocity")
     assert s._dims("dye")[:2] == (Wd, Hd), s._dims("dye")
     return s
@@ -204,7 +206,7 @@ def test_resize_carries_state_like_resizeDoubleFBO(pkg, oracle):
     s = make(pkg, 32, 32, 64, 64)
     s.writeField("velocity", v); s.writeField("dye", dye); s.writeField("pressure", p)
     s.config["SIM_RESOLUTION"] = 48; s.config["DYE_RESOLUTION"] = 96
-    s.canvas = {"width": 512, "height": 512}
+    s.canvas = {"width": 512, "height": 512}; s._sizes = None
     s.initFramebuffers()
     assert bits_equal(s.readField("velocity"), O.resample(v, 48, 48))
     assert bits_equal(s.readField("dye"), O.resample(dye, 96, 96))

@@ -107,7 +107,8 @@ class _Field:
 class FluidSimulation:
     def __init__(self, config: dict | None = None, canvas_width: int = 1024, canvas_height: int = 1024,
                  device: int = -1, flags: int = 0, jacobi_block: int = 0, random=None,
-                 rank: int = 0, world: int = 1, nccl_uid: bytes | None = None):
+                 rank: int = 0, world: int = 1, nccl_uid: bytes | None = None,
+                 sizes: tuple | None = None):
         self.config = default_config()
         if config:
             self.config.update(config)
@@ -121,6 +122,8 @@ class FluidSimulation:
         self._h = C.c_void_p()
         self._device, self._flags, self._jb = device, flags, jacobi_block
         self._rank, self._world, self._uid = rank, world, nccl_uid
+        # test hook: explicit (sim_w, sim_h, dye_w, dye_h) instead of getResolution(config.*)
+        self._sizes = sizes
         self._pushed = {}
         self.velocity = _Field(self, "velocity")
         self.dye = _Field(self, "dye")
@@ -164,6 +167,9 @@ class FluidSimulation:
     def initFramebuffers(self):
         simRes = getResolution(self.config["SIM_RESOLUTION"], self.canvas["width"], self.canvas["height"])
         dyeRes = getResolution(self.config["DYE_RESOLUTION"], self.canvas["width"], self.canvas["height"])
+        if self._sizes is not None:
+            simRes = {"width": self._sizes[0], "height": self._sizes[1]}
+            dyeRes = {"width": self._sizes[2], "height": self._sizes[3]}
         if not self._h:                                  # `dye == null` branch: create
             cfg = Config()
             self._L.fluid_config_default(C.byref(cfg))
