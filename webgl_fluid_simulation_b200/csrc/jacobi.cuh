@@ -107,7 +107,7 @@ struct TB {
     static constexpr int HX = (K + 3) / 4 * 4;       // x halo (columns) on each side of a window
     static constexpr int VALID = 128 - 2 * HX;       // columns a window produces
     static constexpr int RING = K + 1;               // div ring slots (each row stored twice)
-    static constexpr int WARPS = 4;                  // warps per CTA (independent streams)
+    static constexpr int WARPS = 1;                  // one warp per CTA (see jacobi_tb_kernel)
     static constexpr int SMEM_PER_WARP = 2 * RING * 32 * (int)sizeof(float4);
     static constexpr int SMEM = WARPS * SMEM_PER_WARP;
 };
@@ -129,15 +129,70 @@ __device__ __forceinline__ float4 jacobi4(const float4 below, const float4 c, co
     return o;
 }
 
+// One triple of pipeline steps (phases 0,1,2 of the 3-slot window rotation).  EDGE instantiates
+// the wall selects; the caller picks the instantiation with a warp-uniform branch, so the
+// steady-state code carries no select at all.
+template <int K, bool SCALE, bool EDGE>
+__device__ __forceinline__ void tb_triple(float4 (&w)[K][3], float4 (&pf)[3], float4 (&df)[3],
+                                          float4* __restrict__ ring, int& slot,
+                                          const float4* __restrict__ Pg, const float4* __restrict__ Dg,
+                                          float4* __restrict__ Og, const int W4, const int ys,
+                                          const int ye, const int y0, const int y1, const int H,
+                                          const int s0, const bool rev, const bool lane_out,
+                                          const float scale) {
+    using T = TB<K>;
+#pragma unroll
+    for (int ph = 0; ph < 3; ++ph) {
+        const int s = s0 + ph;
+        // ---- level 0: take the prefetched row, start the prefetch three rows ahead ---------------
+        float4 in = rev4(pf[ph], rev);
+        if (SCALE) {
+            in.x = scale * in.x; in.y = scale * in.y; in.z = scale * in.z; in.w = scale * in.w;
+        }
+        const float4 dv = rev4(df[ph], rev);
+        {
+            const int r = min(ys + s + 3, ye);
+            pf[ph] = __ldg(Pg + (size_t)r * W4);
+            df[ph] = __ldg(Dg + (size_t)r * W4);
+        }
+        w[0][(ph + 2) % 3] = in;
+        // park div row (ys+s) in the ring, twice (slot and slot+RING)
+        ring[slot * 32] = dv;
+        ring[(slot + T::RING) * 32] = dv;
+        const float4* rbase = ring + (slot + T::RING) * 32;   // row (ys+s-t) is at rbase[-t*32]
+        // ---- levels 1..K ------------------------------------------------------------------------
+#pragma unroll
+        for (int t = 1; t <= K; ++t) {
+            const int r = ys + s - t;             // row produced by level t at this step
+            const float4 c = w[t - 1][(ph + 1) % 3];
+            float4 below = w[t - 1][(ph + 0) % 3];
+            float4 above = w[t - 1][(ph + 2) % 3];
+            if (EDGE) {                           // warp-uniform conditions
+                if (r == 0) below = c;            // CLAMP_TO_EDGE: p[i,-1] = p[i,0]
+                if (r == H - 1) above = c;        //                p[i,H]  = p[i,H-1]
+            }
+            const float4 d = rbase[-t * 32];
+            const float4 o = jacobi4(below, c, above, d);
+            if (t < K) {
+                w[t][(ph + 2) % 3] = o;
+            } else if (lane_out && r >= y0 && r < y1) {
+                Og[(size_t)r * W4] = o;
+            }
+        }
+        slot = (slot + 1 == T::RING) ? 0 : slot + 1;
+    }
+}
+
+// One warp per CTA: every quantity that steers control flow derives from blockIdx and kernel
+// arguments only, so the compiler can prove the warp converged at each shuffle (no WARPSYNC /
+// BSSY scaffolding) and keeps loop state in uniform registers.
 template <int K, bool SCALE>
-__global__ void __launch_bounds__(TB<K>::WARPS * 32) jacobi_tb_kernel(JacobiArgs a) {
+__global__ void __launch_bounds__(32) jacobi_tb_kernel(JacobiArgs a) {
     using T = TB<K>;
     extern __shared__ float4 smem4[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x;
     const int nxw = (a.W + T::VALID - 1) / T::VALID;
-    const int nch = (a.out_hi - a.out_lo + a.rows_per_chunk - 1) / a.rows_per_chunk;
-    const int wid = blockIdx.x * T::WARPS + warp;
-    if (wid >= nxw * nch) return;                    // whole warp leaves; no block-level sync below
+    const int wid = blockIdx.x;
     const int wx = wid % nxw, cy = wid / nxw;
 
     // ---- x geometry of this lane: mirrored / clamped float4 column group ------------------------
@@ -157,12 +212,13 @@ __global__ void __launch_bounds__(TB<K>::WARPS * 32) jacobi_tb_kernel(JacobiArgs
     const int ye = min(y1 - 1 + K, H - 1);            // last input row (loads clamp to it)
     const int nsteps = y1 - ys + K;                   // level K emits row ys+s-K at step s
 
-    const float4* Pg = reinterpret_cast<const float4*>(a.pin) + (lc >> 2) - (size_t)a.row_off * (W >> 2);
-    const float4* Dg = reinterpret_cast<const float4*>(a.div) + (lc >> 2) - (size_t)a.row_off * (W >> 2);
-    float4* Og = reinterpret_cast<float4*>(a.pout) + (gx >> 2) - (size_t)a.row_off * (W >> 2);
     const int W4 = W >> 2;
+    const ptrdiff_t base = -(ptrdiff_t)a.row_off * W4;
+    const float4* Pg = reinterpret_cast<const float4*>(a.pin) + base + (lc >> 2);
+    const float4* Dg = reinterpret_cast<const float4*>(a.div) + base + (lc >> 2);
+    float4* Og = reinterpret_cast<float4*>(a.pout) + base + (lane_out ? (gx >> 2) : 0);
 
-    float4* ring = smem4 + warp * (2 * T::RING * 32) + lane;   // slot k at ring[k*32]
+    float4* ring = smem4 + lane;                      // slot k at ring[k*32]
 
     // rotating windows: w[t][(ph+0)%3] = row r-1, [(ph+1)%3] = row r, [(ph+2)%3] = fresh row r+1
     float4 w[K][3];
@@ -184,49 +240,12 @@ __global__ void __launch_bounds__(TB<K>::WARPS * 32) jacobi_tb_kernel(JacobiArgs
     for (int s0 = 0; s0 < nsteps; s0 += 3) {
         // does any row this triple touches lie on the bottom / top wall?
         const int lo = ys + s0 - K, hi = ys + s0 + 2;
-        const bool edge = (lo <= 0) || (hi >= H - 1);
-#pragma unroll
-        for (int ph = 0; ph < 3; ++ph) {
-            const int s = s0 + ph;
-            // ---- level 0: take the prefetched row, start the prefetch three rows ahead -----------
-            float4 in = rev4(pf[ph], rev);
-            if (SCALE) {
-                in.x = a.scale * in.x; in.y = a.scale * in.y;
-                in.z = a.scale * in.z; in.w = a.scale * in.w;
-            }
-            const float4 dv = rev4(df[ph], rev);
-            {
-                const int r = min(ys + s + 3, ye);
-                pf[ph] = __ldg(Pg + (size_t)r * W4);
-                df[ph] = __ldg(Dg + (size_t)r * W4);
-            }
-            w[0][(ph + 2) % 3] = in;
-            // park div row (ys+s) in the ring, twice (slot and slot+RING)
-            ring[slot * 32] = dv;
-            ring[(slot + T::RING) * 32] = dv;
-            const float4* rbase = ring + (slot + T::RING) * 32;   // row (ys+s-t) is at rbase[-t*32]
-
-            // ---- levels 1..K --------------------------------------------------------------------
-#pragma unroll
-            for (int t = 1; t <= K; ++t) {
-                const int r = ys + s - t;             // row produced by level t at this step
-                const float4 c = w[t - 1][(ph + 1) % 3];
-                float4 below = w[t - 1][(ph + 0) % 3];
-                float4 above = w[t - 1][(ph + 2) % 3];
-                if (edge) {                           // warp-uniform
-                    if (r == 0) below = c;            // CLAMP_TO_EDGE: p[i,-1] = p[i,0]
-                    if (r == H - 1) above = c;        //                p[i,H]  = p[i,H-1]
-                }
-                const float4 d = rbase[-t * 32];
-                const float4 o = jacobi4(below, c, above, d);
-                if (t < K) {
-                    w[t][(ph + 2) % 3] = o;
-                } else if (lane_out && r >= y0 && r < y1) {
-                    Og[(size_t)r * W4] = o;
-                }
-            }
-            slot = (slot + 1 == T::RING) ? 0 : slot + 1;
-        }
+        if ((lo <= 0) || (hi >= H - 1))
+            tb_triple<K, SCALE, true>(w, pf, df, ring, slot, Pg, Dg, Og, W4, ys, ye, y0, y1, H, s0,
+                                      rev, lane_out, a.scale);
+        else
+            tb_triple<K, SCALE, false>(w, pf, df, ring, slot, Pg, Dg, Og, W4, ys, ye, y0, y1, H, s0,
+                                       rev, lane_out, a.scale);
     }
 }
 
