@@ -116,58 +116,95 @@ __device__ __forceinline__ float4 rev4(float4 v, bool rev) {
     return rev ? make_float4(v.w, v.z, v.y, v.x) : v;
 }
 
-// one Jacobi update of a float4 of row `c`, with rows below/above and the shuffled neighbours
+// Blackwell packed fp32 arithmetic (FADD2 / FMUL2): two IEEE round-to-nearest results per issue
+// slot.  The kernel is issue-bound, so the vertical part of the stencil (+below, +above, -div,
+// *0.25 — element-wise on the (x,y) and (z,w) halves of a float4) is issued packed; the
+// horizontal sums need the misaligned pair (y,z) and stay scalar.  Rounding is per element and
+// identical to the scalar form, so results remain bit-identical to the reference expression.
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pack2(float a, float b) {
+    u64 v; asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(a), "f"(b)); return v;
+}
+__device__ __forceinline__ void unpack2(u64 v, float& a, float& b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+    u64 c; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(c) : "l"(a), "l"(b)); return c;
+}
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
+    u64 c; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(c) : "l"(a), "l"(b)); return c;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+    u64 c; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(c) : "l"(a), "l"(b)); return c;
+}
+
+// one Jacobi update of a float4 of row `c`, with rows below/above and the shuffled neighbours:
+//   o = ((((L + R) + below) + above) - d) * 0.25   per column, in that order
 __device__ __forceinline__ float4 jacobi4(const float4 below, const float4 c, const float4 above,
                                           const float4 d) {
     const float l = __shfl_up_sync(0xffffffffu, c.w, 1);
     const float r = __shfl_down_sync(0xffffffffu, c.x, 1);
+    const u64 q = pack2(0.25f, 0.25f);
+    u64 lo = pack2(l + c.y, c.x + c.z);
+    u64 hi = pack2(c.y + c.w, c.z + r);
+    lo = add2(lo, pack2(below.x, below.y));
+    hi = add2(hi, pack2(below.z, below.w));
+    lo = add2(lo, pack2(above.x, above.y));
+    hi = add2(hi, pack2(above.z, above.w));
+    lo = sub2(lo, pack2(d.x, d.y));
+    hi = sub2(hi, pack2(d.z, d.w));
+    lo = mul2(lo, q);
+    hi = mul2(hi, q);
     float4 o;
-    o.x = ((((l + c.y) + below.x) + above.x) - d.x) * 0.25f;
-    o.y = ((((c.x + c.z) + below.y) + above.y) - d.y) * 0.25f;
-    o.z = ((((c.y + c.w) + below.z) + above.z) - d.z) * 0.25f;
-    o.w = ((((c.z + r) + below.w) + above.w) - d.w) * 0.25f;
+    unpack2(lo, o.x, o.y);
+    unpack2(hi, o.z, o.w);
     return o;
 }
 
+// Per-warp stream state that survives across triples.
+struct TBStream {
+    const float4* pl;    // next p row to prefetch (this lane's float4 column group)
+    const float4* dl;    // next div row to prefetch
+    float4* op;          // where level K's row of THIS step goes (advances one row per step)
+    int rload;           // global row index pl/dl point at
+    int rout;            // global row index op points at  (= ys + s - K)
+    int slot;            // div ring slot of the row consumed at this step
+};
+
 // One triple of pipeline steps (phases 0,1,2 of the 3-slot window rotation).  EDGE instantiates
-// the wall selects; the caller picks the instantiation with a warp-uniform branch, so the
-// steady-state code carries no select at all.
-template <int K, bool SCALE, bool EDGE>
+// the wall selects in y, REV the mirrored-lane reversal in x; both are chosen by warp-uniform
+// branches OUTSIDE the steady-state loop, which therefore carries no select and no MOV.
+template <int K, bool SCALE, bool EDGE, bool REV>
 __device__ __forceinline__ void tb_triple(float4 (&w)[K][3], float4 (&pf)[3], float4 (&df)[3],
-                                          float4* __restrict__ ring, int& slot,
-                                          const float4* __restrict__ Pg, const float4* __restrict__ Dg,
-                                          float4* __restrict__ Og, const int W4, const int ys,
+                                          float4* __restrict__ ring, TBStream& st, const int W4,
                                           const int ye, const int y0, const int y1, const int H,
-                                          const int s0, const bool rev, const bool lane_out,
-                                          const float scale) {
+                                          const bool rev, const bool lane_out, const float scale) {
     using T = TB<K>;
 #pragma unroll
     for (int ph = 0; ph < 3; ++ph) {
-        const int s = s0 + ph;
         // ---- level 0: take the prefetched row, start the prefetch three rows ahead ---------------
-        float4 in = rev4(pf[ph], rev);
+        float4 in = pf[ph];
+        float4 dv = df[ph];
+        if (REV) { in = rev4(in, rev); dv = rev4(dv, rev); }
         if (SCALE) {
             in.x = scale * in.x; in.y = scale * in.y; in.z = scale * in.z; in.w = scale * in.w;
         }
-        const float4 dv = rev4(df[ph], rev);
-        {
-            const int r = min(ys + s + 3, ye);
-            pf[ph] = __ldg(Pg + (size_t)r * W4);
-            df[ph] = __ldg(Dg + (size_t)r * W4);
-        }
+        pf[ph] = __ldg(st.pl);
+        df[ph] = __ldg(st.dl);
+        if (st.rload < ye) { ++st.rload; st.pl += W4; st.dl += W4; }   // loads clamp to row ye
         w[0][(ph + 2) % 3] = in;
-        // park div row (ys+s) in the ring, twice (slot and slot+RING)
-        ring[slot * 32] = dv;
-        ring[(slot + T::RING) * 32] = dv;
-        const float4* rbase = ring + (slot + T::RING) * 32;   // row (ys+s-t) is at rbase[-t*32]
+        // park this div row in the ring, twice (slot and slot+RING)
+        ring[st.slot * 32] = dv;
+        ring[(st.slot + T::RING) * 32] = dv;
+        const float4* rbase = ring + (st.slot + T::RING) * 32;   // row (r0 - t) is at rbase[-t*32]
         // ---- levels 1..K ------------------------------------------------------------------------
 #pragma unroll
         for (int t = 1; t <= K; ++t) {
-            const int r = ys + s - t;             // row produced by level t at this step
             const float4 c = w[t - 1][(ph + 1) % 3];
             float4 below = w[t - 1][(ph + 0) % 3];
             float4 above = w[t - 1][(ph + 2) % 3];
             if (EDGE) {                           // warp-uniform conditions
+                const int r = st.rout + (K - t);  // row produced by level t at this step
                 if (r == 0) below = c;            // CLAMP_TO_EDGE: p[i,-1] = p[i,0]
                 if (r == H - 1) above = c;        //                p[i,H]  = p[i,H-1]
             }
@@ -175,11 +212,69 @@ __device__ __forceinline__ void tb_triple(float4 (&w)[K][3], float4 (&pf)[3], fl
             const float4 o = jacobi4(below, c, above, d);
             if (t < K) {
                 w[t][(ph + 2) % 3] = o;
-            } else if (lane_out && r >= y0 && r < y1) {
-                Og[(size_t)r * W4] = o;
+            } else if (lane_out && st.rout >= y0 && st.rout < y1) {
+                *st.op = o;
             }
         }
-        slot = (slot + 1 == T::RING) ? 0 : slot + 1;
+        st.slot = (st.slot + 1 == T::RING) ? 0 : st.slot + 1;
+        ++st.rout;
+        st.op += W4;
+    }
+}
+
+template <int K, bool SCALE, bool REV>
+__device__ __forceinline__ void tb_stream(const JacobiArgs& a, float4* __restrict__ ring,
+                                          const int lc, const int gx, const bool rev,
+                                          const bool lane_out, const int cy) {
+    const int W = a.W, H = a.H, W4 = W >> 2;
+    // ---- y geometry of this warp's stream ----------------------------------------------------------
+    const int y0 = a.out_lo + cy * a.rows_per_chunk;
+    const int y1 = min(y0 + a.rows_per_chunk, a.out_hi);
+    const int ys = max(y0 - K, 0);                    // first input row
+    const int ye = min(y1 - 1 + K, H - 1);            // last input row (loads clamp to it)
+    const int nsteps = y1 - ys + K;                   // level K emits row ys+s-K at step s
+
+    const ptrdiff_t base = -(ptrdiff_t)a.row_off * W4;
+    const float4* Pg = reinterpret_cast<const float4*>(a.pin) + base + (lc >> 2);
+    const float4* Dg = reinterpret_cast<const float4*>(a.div) + base + (lc >> 2);
+    float4* Og = reinterpret_cast<float4*>(a.pout) + base + (lane_out ? (gx >> 2) : 0);
+
+    // rotating windows: w[t][(ph+0)%3] = row r-1, [(ph+1)%3] = row r, [(ph+2)%3] = fresh row r+1
+    float4 w[K][3];
+#pragma unroll
+    for (int t = 0; t < K; ++t)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) w[t][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    // prefetch buffers, three rows ahead
+    float4 pf[3], df[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const int r = min(ys + q, ye);
+        pf[q] = __ldg(Pg + (ptrdiff_t)r * W4);
+        df[q] = __ldg(Dg + (ptrdiff_t)r * W4);
+    }
+    TBStream st;
+    st.rload = min(ys + 3, ye);
+    st.pl = Pg + (ptrdiff_t)st.rload * W4;
+    st.dl = Dg + (ptrdiff_t)st.rload * W4;
+    st.rout = ys - K;
+    st.op = Og + (ptrdiff_t)st.rout * W4;             // only dereferenced for rows in [y0, y1)
+    st.slot = 0;
+
+    // A triple touches a wall row when its rows [ys+s0-K, ys+s0+2] reach row 0 or row H-1: the
+    // first triples of a bottom chunk and the last ones of a top chunk.  Wall and steady-state
+    // triples run in SEPARATE loops (not one loop with a branch) so that the steady-state loop
+    // has its own register assignment and its 3-phase rotation closes without a single MOV.
+    int s0 = 0;
+#pragma unroll 1
+    for (int part = 0; part < 2; ++part) {
+#pragma unroll 1
+        for (; s0 < nsteps && ((ys + s0 - K <= 0) || (ys + s0 + 2 >= H - 1)); s0 += 3)
+            tb_triple<K, SCALE, true, REV>(w, pf, df, ring, st, W4, ye, y0, y1, H, rev, lane_out, a.scale);
+#pragma unroll 1
+        for (; s0 < nsteps && !((ys + s0 - K <= 0) || (ys + s0 + 2 >= H - 1)); s0 += 3)
+            tb_triple<K, SCALE, false, REV>(w, pf, df, ring, st, W4, ye, y0, y1, H, rev, lane_out, a.scale);
     }
 }
 
@@ -196,57 +291,18 @@ __global__ void __launch_bounds__(32) jacobi_tb_kernel(JacobiArgs a) {
     const int wx = wid % nxw, cy = wid / nxw;
 
     // ---- x geometry of this lane: mirrored / clamped float4 column group ------------------------
-    const int W = a.W, H = a.H;
+    const int W = a.W;
     const int gx = wx * T::VALID - T::HX + 4 * lane;  // first global column of this lane
     int lc = gx;
     bool rev = false;
     if (gx < 0) { lc = -gx - 4; rev = true; }                 // p[-1-m] = p[m]
     else if (gx >= W) { lc = 2 * W - 4 - gx; rev = true; }    // p[W+m]  = p[W-1-m]
     lc = min(max(lc, 0), W - 4);
+    const bool any_rev = (wx == 0) || ((wx + 1) * T::VALID + T::HX > W);   // warp-uniform
     const bool lane_out = (lane >= T::HX / 4) && (lane < 32 - T::HX / 4) && (gx >= 0) && (gx < W);
-
-    // ---- y geometry of this warp's stream ----------------------------------------------------------
-    const int y0 = a.out_lo + cy * a.rows_per_chunk;
-    const int y1 = min(y0 + a.rows_per_chunk, a.out_hi);
-    const int ys = max(y0 - K, 0);                    // first input row
-    const int ye = min(y1 - 1 + K, H - 1);            // last input row (loads clamp to it)
-    const int nsteps = y1 - ys + K;                   // level K emits row ys+s-K at step s
-
-    const int W4 = W >> 2;
-    const ptrdiff_t base = -(ptrdiff_t)a.row_off * W4;
-    const float4* Pg = reinterpret_cast<const float4*>(a.pin) + base + (lc >> 2);
-    const float4* Dg = reinterpret_cast<const float4*>(a.div) + base + (lc >> 2);
-    float4* Og = reinterpret_cast<float4*>(a.pout) + base + (lane_out ? (gx >> 2) : 0);
-
     float4* ring = smem4 + lane;                      // slot k at ring[k*32]
-
-    // rotating windows: w[t][(ph+0)%3] = row r-1, [(ph+1)%3] = row r, [(ph+2)%3] = fresh row r+1
-    float4 w[K][3];
-#pragma unroll
-    for (int t = 0; t < K; ++t)
-#pragma unroll
-        for (int q = 0; q < 3; ++q) w[t][q] = make_float4(0.f, 0.f, 0.f, 0.f);
-
-    // prefetch buffers, three rows ahead
-    float4 pf[3], df[3];
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {
-        const int r = min(ys + q, ye);
-        pf[q] = __ldg(Pg + (size_t)r * W4);
-        df[q] = __ldg(Dg + (size_t)r * W4);
-    }
-
-    int slot = 0;                                     // ring slot of the row loaded at this step
-    for (int s0 = 0; s0 < nsteps; s0 += 3) {
-        // does any row this triple touches lie on the bottom / top wall?
-        const int lo = ys + s0 - K, hi = ys + s0 + 2;
-        if ((lo <= 0) || (hi >= H - 1))
-            tb_triple<K, SCALE, true>(w, pf, df, ring, slot, Pg, Dg, Og, W4, ys, ye, y0, y1, H, s0,
-                                      rev, lane_out, a.scale);
-        else
-            tb_triple<K, SCALE, false>(w, pf, df, ring, slot, Pg, Dg, Og, W4, ys, ye, y0, y1, H, s0,
-                                       rev, lane_out, a.scale);
-    }
+    if (any_rev) tb_stream<K, SCALE, true>(a, ring, lc, gx, rev, lane_out, cy);
+    else tb_stream<K, SCALE, false>(a, ring, lc, gx, rev, lane_out, cy);
 }
 
 }  // namespace fk
