@@ -1,6 +1,6 @@
 """Lane-level numpy model of csrc/jacobi.cuh::jacobi_tb_kernel — same window geometry, mirrored
-loads, 3-slot rotating windows, doubled div ring, wall selects, chunking and store predicate,
-statement for statement.  It exists so the kernel's index logic can be checked against the oracle
+loads, 3-slot rotating windows, RD-slot div register ring, U-step unrolled blocks, wall selects,
+chunking and store predicate, statement for statement.  It exists so the kernel's index logic can be checked against the oracle
 on a machine without a GPU (tests/test_jacobi_tb_model.py); it is not used by the product."""
 import numpy as np
 
@@ -32,7 +32,7 @@ def jacobi_tb_model(pin, div, K, rows_per_chunk, scale=None, row_off=0, out_lo=N
     H = rows_local if H is None else H
     out_lo = 0 if out_lo is None else out_lo
     out_hi = H if out_hi is None else out_hi
-    HX = (K + 3) // 4 * 4; VALID = 128 - 2 * HX; RING = K + 1
+    HX = (K + 3) // 4 * 4; VALID = 128 - 2 * HX; RD = (K + 1 + 2) // 3 * 3; U = RD
     assert W % 4 == 0 and W >= 16
     if pout is None:
         pout = np.full_like(pin, np.nan)
@@ -59,39 +59,38 @@ def jacobi_tb_model(pin, div, K, rows_per_chunk, scale=None, row_off=0, out_lo=N
             return v.astype(F)
 
         w = np.zeros((K, 3, 32, 4), F)
-        ring = np.full((2 * RING, 32, 4), np.nan, F)
+        dr = np.full((RD, 32, 4), np.nan, F)
         pf = [load(pin, min(ys + q, ye)) for q in range(3)]
         df = [load(div, min(ys + q, ye)) for q in range(3)]
-        slot = 0
-        for s0 in range(0, nsteps, 3):
-            lo, hi = ys + s0 - K, ys + s0 + 2
-            edge = (lo <= 0) or (hi >= H - 1)
-            for ph in range(3):
-                s = s0 + ph
-                inn = pf[ph].copy()
+        rload = min(ys + 3, ye)
+        rout = ys - K
+        for s0 in range(0, nsteps, U):
+            edge = (ys + s0 - K <= 0) or (ys + s0 + U - 1 >= H - 1)
+            for ph in range(U):
+                inn = pf[ph % 3].copy()
                 if scale is not None:
                     inn = F(scale) * inn
-                dv = df[ph].copy()
-                r = min(ys + s + 3, ye)
-                pf[ph] = load(pin, r); df[ph] = load(div, r)
+                dv = df[ph % 3].copy()
+                pf[ph % 3] = load(pin, rload); df[ph % 3] = load(div, rload)
+                if rload < ye:
+                    rload += 1
                 w[0, (ph + 2) % 3] = inn
-                ring[slot] = dv; ring[slot + RING] = dv
-                rbase = slot + RING
+                dr[ph % RD] = dv
                 for t in range(1, K + 1):
-                    r = ys + s - t
                     c = w[t - 1, (ph + 1) % 3]
                     below = w[t - 1, (ph + 0) % 3]
                     above = w[t - 1, (ph + 2) % 3]
                     if edge:
+                        r = rout + (K - t)
                         if r == 0: below = c
                         if r == H - 1: above = c
-                    d = ring[rbase - t]
+                    d = dr[(ph - t + RD) % RD]
                     with np.errstate(invalid="ignore"):
                         o = _jacobi4(below, c, above, d)
                     if t < K:
                         w[t, (ph + 2) % 3] = o
-                    elif y0 <= r < y1:
+                    elif y0 <= rout < y1:
                         for l in np.nonzero(lane_out)[0]:
-                            pout[r - row_off, gx[l]:gx[l] + 4] = o[l]
-                slot = 0 if slot + 1 == RING else slot + 1
+                            pout[rout - row_off, gx[l]:gx[l] + 4] = o[l]
+                rout += 1
     return pout

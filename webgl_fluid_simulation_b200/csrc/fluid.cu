@@ -97,22 +97,14 @@ int check_launch(fluid_t* h, const char* what, int n = 1) {
 
 // ---- Jacobi dispatch -----------------------------------------------------------------------------
 
-constexpr int KMAX = 10;
+constexpr int KMAX = 12;
 
 template <int K, bool SCALE>
 int launch_tb(fluid_t* h, const JacobiArgs& a) {
     using T = TB<K>;
-    static bool attr_set[64] = {};
-    auto kern = jacobi_tb_kernel<K, SCALE>;
-    if (!attr_set[h->device & 63]) {
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM));
-        attr_set[h->device & 63] = true;
-    }
     const int nxw = (a.W + T::VALID - 1) / T::VALID;
     const int nch = (a.out_hi - a.out_lo + a.rows_per_chunk - 1) / a.rows_per_chunk;
-    const int nwarps = nxw * nch;
-    const int blocks = (nwarps + T::WARPS - 1) / T::WARPS;
-    kern<<<blocks, T::WARPS * 32, T::SMEM, h->stream>>>(a);
+    jacobi_tb_kernel<K, SCALE><<<nxw * nch, 32, 0, h->stream>>>(a);   // one warp per CTA
     return check_launch(h, "jacobi_tb_kernel");
 }
 
@@ -121,20 +113,23 @@ int launch_tb_k(fluid_t* h, const JacobiArgs& a, bool scale) {
     return scale ? launch_tb<K, true>(h, a) : launch_tb<K, false>(h, a);
 }
 
-// rows per warp stream: enough chunks that every SM holds `target` warps, single wave
+// rows per warp stream: enough chunks that every SM holds its full complement of resident warps
+// (single wave), rounded so that a stream's step count R + 2K is a multiple of the unroll U.
 template <int K>
 int tb_rows(const fluid_t* h, int W, int rows) {
     if (h->jacobi_rows_override > 0) return h->jacobi_rows_override;
     using T = TB<K>;
     const int nxw = (W + T::VALID - 1) / T::VALID;
     int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, jacobi_tb_kernel<K, false>, T::WARPS * 32,
-                                                  T::SMEM);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, jacobi_tb_kernel<K, false>, 32, 0);
     if (occ < 1) occ = 1;
-    const int resident_warps = h->sm_count * occ * T::WARPS;
-    int nch = std::max(1, resident_warps / nxw);
+    const int resident_warps = h->sm_count * occ;
+    const int nch = std::max(1, resident_warps / nxw);
     int r = (rows + nch - 1) / nch;
     r = std::max(r, 4 * K);                 // keep the 2K warm-up rows a bounded fraction
+    // round R up so that (R + 2K) % U == 0: no partially wasted unrolled block
+    const int rem = (r + 2 * K) % T::U;
+    if (rem) r += T::U - rem;
     return std::min(r, rows);
 }
 
@@ -142,7 +137,7 @@ int launch_tb_dyn(fluid_t* h, int K, JacobiArgs a, bool scale) {
     const int rows = a.out_hi - a.out_lo;
     switch (K) {
 #define CASE(KK) case KK: a.rows_per_chunk = tb_rows<KK>(h, a.W, rows); return launch_tb_k<KK>(h, a, scale);
-        CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10)
+        CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12)
 #undef CASE
     }
     return fail(h, FLUID_ERR_INVALID, "temporal block depth %d out of range", K);

@@ -20,10 +20,9 @@
 //       symmetric in B/T, so rows 0 and H-1 select "below := centre" / "above := centre"
 //       explicitly (EDGE instantiation, only on the few steps that touch those rows);
 //     * div[r] is needed by level t when it produces row r, i.e. K times at K different steps:
-//       each lane parks its float4 of the row in a shared-memory ring it alone reads back
-//       (conflict-free LDS.128; smem is used as a software-managed per-lane spill ring).  Every
-//       row is written twice, RING slots apart, so all K reads use one base register plus a
-//       compile-time immediate offset;
+//       each lane keeps its float4 of the last RD rows in a statically indexed register ring
+//       (the step loop is unrolled RD times, so ring slots are compile-time register names);
+//       no shared memory is used at all — the LSU data pipe only carries the shuffles;
 //     * p / div rows are prefetched three steps ahead into registers (coalesced 512 B per warp
 //       row segment, LDG.128).
 //   The optional SCALE template fuses the clear pass (S:1253-1257, p <- PRESSURE*p) into the
@@ -106,10 +105,8 @@ template <int K>
 struct TB {
     static constexpr int HX = (K + 3) / 4 * 4;       // x halo (columns) on each side of a window
     static constexpr int VALID = 128 - 2 * HX;       // columns a window produces
-    static constexpr int RING = K + 1;               // div ring slots (each row stored twice)
-    static constexpr int WARPS = 1;                  // one warp per CTA (see jacobi_tb_kernel)
-    static constexpr int SMEM_PER_WARP = 2 * RING * 32 * (int)sizeof(float4);
-    static constexpr int SMEM = WARPS * SMEM_PER_WARP;
+    static constexpr int RD = (K + 1 + 2) / 3 * 3;   // div register-ring slots (multiple of 3, > K)
+    static constexpr int U = RD;                     // pipeline steps per unrolled block
 };
 
 __device__ __forceinline__ float4 rev4(float4 v, bool rev) {
@@ -161,42 +158,43 @@ __device__ __forceinline__ float4 jacobi4(const float4 below, const float4 c, co
     return o;
 }
 
-// Per-warp stream state that survives across triples.
+// Per-warp stream state that survives across unrolled blocks.
 struct TBStream {
     const float4* pl;    // next p row to prefetch (this lane's float4 column group)
     const float4* dl;    // next div row to prefetch
     float4* op;          // where level K's row of THIS step goes (advances one row per step)
     int rload;           // global row index pl/dl point at
     int rout;            // global row index op points at  (= ys + s - K)
-    int slot;            // div ring slot of the row consumed at this step
 };
 
-// One triple of pipeline steps (phases 0,1,2 of the 3-slot window rotation).  EDGE instantiates
-// the wall selects in y, REV the mirrored-lane reversal in x; both are chosen by warp-uniform
-// branches OUTSIDE the steady-state loop, which therefore carries no select and no MOV.
+// One unrolled block of U pipeline steps.  All register "rings" are indexed with compile-time
+// constants: the 3-slot p windows rotate with period 3, the div ring dr[RD] with period RD = U,
+// so after one block every value sits in the register it started in and the steady-state loop
+// closes without moves.  (div[r] is consumed by level t when it produces row r, i.e. at K
+// different steps; an earlier version parked it in a shared-memory ring, which made the LSU data
+// pipe — 4 wavefronts per LDS.128 — the bottleneck.  Registers have no such port limit.)
+// EDGE instantiates the wall selects in y, REV the mirrored-lane reversal in x; both are chosen
+// by warp-uniform branches OUTSIDE the steady-state loop.
 template <int K, bool SCALE, bool EDGE, bool REV>
-__device__ __forceinline__ void tb_triple(float4 (&w)[K][3], float4 (&pf)[3], float4 (&df)[3],
-                                          float4* __restrict__ ring, TBStream& st, const int W4,
-                                          const int ye, const int y0, const int y1, const int H,
-                                          const bool rev, const bool lane_out, const float scale) {
+__device__ __forceinline__ void tb_block(float4 (&w)[K][3], float4 (&pf)[3], float4 (&df)[3],
+                                         float4 (&dr)[TB<K>::RD], TBStream& st, const int W4,
+                                         const int ye, const int y0, const int y1, const int H,
+                                         const bool rev, const bool lane_out, const float scale) {
     using T = TB<K>;
 #pragma unroll
-    for (int ph = 0; ph < 3; ++ph) {
+    for (int ph = 0; ph < T::U; ++ph) {
         // ---- level 0: take the prefetched row, start the prefetch three rows ahead ---------------
-        float4 in = pf[ph];
-        float4 dv = df[ph];
+        float4 in = pf[ph % 3];
+        float4 dv = df[ph % 3];
         if (REV) { in = rev4(in, rev); dv = rev4(dv, rev); }
         if (SCALE) {
             in.x = scale * in.x; in.y = scale * in.y; in.z = scale * in.z; in.w = scale * in.w;
         }
-        pf[ph] = __ldg(st.pl);
-        df[ph] = __ldg(st.dl);
+        pf[ph % 3] = __ldg(st.pl);
+        df[ph % 3] = __ldg(st.dl);
         if (st.rload < ye) { ++st.rload; st.pl += W4; st.dl += W4; }   // loads clamp to row ye
         w[0][(ph + 2) % 3] = in;
-        // park this div row in the ring, twice (slot and slot+RING)
-        ring[st.slot * 32] = dv;
-        ring[(st.slot + T::RING) * 32] = dv;
-        const float4* rbase = ring + (st.slot + T::RING) * 32;   // row (r0 - t) is at rbase[-t*32]
+        dr[ph % T::RD] = dv;
         // ---- levels 1..K ------------------------------------------------------------------------
 #pragma unroll
         for (int t = 1; t <= K; ++t) {
@@ -208,7 +206,7 @@ __device__ __forceinline__ void tb_triple(float4 (&w)[K][3], float4 (&pf)[3], fl
                 if (r == 0) below = c;            // CLAMP_TO_EDGE: p[i,-1] = p[i,0]
                 if (r == H - 1) above = c;        //                p[i,H]  = p[i,H-1]
             }
-            const float4 d = rbase[-t * 32];
+            const float4 d = dr[(ph - t + T::RD) % T::RD];   // div row loaded t steps ago
             const float4 o = jacobi4(below, c, above, d);
             if (t < K) {
                 w[t][(ph + 2) % 3] = o;
@@ -216,16 +214,15 @@ __device__ __forceinline__ void tb_triple(float4 (&w)[K][3], float4 (&pf)[3], fl
                 *st.op = o;
             }
         }
-        st.slot = (st.slot + 1 == T::RING) ? 0 : st.slot + 1;
         ++st.rout;
         st.op += W4;
     }
 }
 
 template <int K, bool SCALE, bool REV>
-__device__ __forceinline__ void tb_stream(const JacobiArgs& a, float4* __restrict__ ring,
-                                          const int lc, const int gx, const bool rev,
-                                          const bool lane_out, const int cy) {
+__device__ __forceinline__ void tb_stream(const JacobiArgs& a, const int lc, const int gx,
+                                          const bool rev, const bool lane_out, const int cy) {
+    using T = TB<K>;
     const int W = a.W, H = a.H, W4 = W >> 2;
     // ---- y geometry of this warp's stream ----------------------------------------------------------
     const int y0 = a.out_lo + cy * a.rows_per_chunk;
@@ -245,6 +242,9 @@ __device__ __forceinline__ void tb_stream(const JacobiArgs& a, float4* __restric
     for (int t = 0; t < K; ++t)
 #pragma unroll
         for (int q = 0; q < 3; ++q) w[t][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 dr[T::RD];
+#pragma unroll
+    for (int q = 0; q < T::RD; ++q) dr[q] = make_float4(0.f, 0.f, 0.f, 0.f);
 
     // prefetch buffers, three rows ahead
     float4 pf[3], df[3];
@@ -260,21 +260,20 @@ __device__ __forceinline__ void tb_stream(const JacobiArgs& a, float4* __restric
     st.dl = Dg + (ptrdiff_t)st.rload * W4;
     st.rout = ys - K;
     st.op = Og + (ptrdiff_t)st.rout * W4;             // only dereferenced for rows in [y0, y1)
-    st.slot = 0;
 
-    // A triple touches a wall row when its rows [ys+s0-K, ys+s0+2] reach row 0 or row H-1: the
-    // first triples of a bottom chunk and the last ones of a top chunk.  Wall and steady-state
-    // triples run in SEPARATE loops (not one loop with a branch) so that the steady-state loop
-    // has its own register assignment and its 3-phase rotation closes without a single MOV.
+    // A block touches a wall row when its rows [ys+s0-K, ys+s0+U-1] reach row 0 or row H-1: the
+    // first blocks of a bottom chunk and the last ones of a top chunk.  Wall and steady-state
+    // blocks run in SEPARATE loops (not one loop with a branch) so that the steady-state loop
+    // has its own register assignment and its rotations close without a single MOV.
     int s0 = 0;
 #pragma unroll 1
     for (int part = 0; part < 2; ++part) {
 #pragma unroll 1
-        for (; s0 < nsteps && ((ys + s0 - K <= 0) || (ys + s0 + 2 >= H - 1)); s0 += 3)
-            tb_triple<K, SCALE, true, REV>(w, pf, df, ring, st, W4, ye, y0, y1, H, rev, lane_out, a.scale);
+        for (; s0 < nsteps && ((ys + s0 - K <= 0) || (ys + s0 + T::U - 1 >= H - 1)); s0 += T::U)
+            tb_block<K, SCALE, true, REV>(w, pf, df, dr, st, W4, ye, y0, y1, H, rev, lane_out, a.scale);
 #pragma unroll 1
-        for (; s0 < nsteps && !((ys + s0 - K <= 0) || (ys + s0 + 2 >= H - 1)); s0 += 3)
-            tb_triple<K, SCALE, false, REV>(w, pf, df, ring, st, W4, ye, y0, y1, H, rev, lane_out, a.scale);
+        for (; s0 < nsteps && !((ys + s0 - K <= 0) || (ys + s0 + T::U - 1 >= H - 1)); s0 += T::U)
+            tb_block<K, SCALE, false, REV>(w, pf, df, dr, st, W4, ye, y0, y1, H, rev, lane_out, a.scale);
     }
 }
 
@@ -284,7 +283,6 @@ __device__ __forceinline__ void tb_stream(const JacobiArgs& a, float4* __restric
 template <int K, bool SCALE>
 __global__ void __launch_bounds__(32) jacobi_tb_kernel(JacobiArgs a) {
     using T = TB<K>;
-    extern __shared__ float4 smem4[];
     const int lane = threadIdx.x;
     const int nxw = (a.W + T::VALID - 1) / T::VALID;
     const int wid = blockIdx.x;
@@ -300,9 +298,8 @@ __global__ void __launch_bounds__(32) jacobi_tb_kernel(JacobiArgs a) {
     lc = min(max(lc, 0), W - 4);
     const bool any_rev = (wx == 0) || ((wx + 1) * T::VALID + T::HX > W);   // warp-uniform
     const bool lane_out = (lane >= T::HX / 4) && (lane < 32 - T::HX / 4) && (gx >= 0) && (gx < W);
-    float4* ring = smem4 + lane;                      // slot k at ring[k*32]
-    if (any_rev) tb_stream<K, SCALE, true>(a, ring, lc, gx, rev, lane_out, cy);
-    else tb_stream<K, SCALE, false>(a, ring, lc, gx, rev, lane_out, cy);
+    if (any_rev) tb_stream<K, SCALE, true>(a, lc, gx, rev, lane_out, cy);
+    else tb_stream<K, SCALE, false>(a, lc, gx, rev, lane_out, cy);
 }
 
 }  // namespace fk
