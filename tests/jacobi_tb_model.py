@@ -1,5 +1,5 @@
 """Lane-level numpy model of csrc/jacobi.cuh::jacobi_tb_kernel — same window geometry, mirrored
-loads, 3-slot rotating windows, RD-slot div register ring, U-step unrolled blocks, wall selects,
+loads, D-deep staging ring, 3-slot rotating windows, shifted K+3-slot div register ring, wall selects,
 chunking and store predicate, statement for statement.  It exists so the kernel's index logic can be checked against the oracle
 on a machine without a GPU (tests/test_jacobi_tb_model.py); it is not used by the product."""
 import numpy as np
@@ -32,7 +32,7 @@ def jacobi_tb_model(pin, div, K, rows_per_chunk, scale=None, row_off=0, out_lo=N
     H = rows_local if H is None else H
     out_lo = 0 if out_lo is None else out_lo
     out_hi = H if out_hi is None else out_hi
-    HX = (K + 3) // 4 * 4; VALID = 128 - 2 * HX; RD = (K + 1 + 2) // 3 * 3; U = RD
+    HX = (K + 3) // 4 * 4; VALID = 128 - 2 * HX; RD = K + 3; U = 3; D = 8
     assert W % 4 == 0 and W >= 16
     if pout is None:
         pout = np.full_like(pin, np.nan)
@@ -60,22 +60,27 @@ def jacobi_tb_model(pin, div, K, rows_per_chunk, scale=None, row_off=0, out_lo=N
 
         w = np.zeros((K, 3, 32, 4), F)
         dr = np.full((RD, 32, 4), np.nan, F)
-        pf = [load(pin, min(ys + q, ye)) for q in range(3)]
-        df = [load(div, min(ys + q, ye)) for q in range(3)]
-        rload = min(ys + 3, ye)
+        # staging ring: rows ys .. ys+D-1 (clamped to ye)
+        rload = ys
+        stage_p, stage_d = [None] * D, [None] * D
+        for q in range(D):
+            stage_p[q] = load(pin, rload); stage_d[q] = load(div, rload)
+            if rload < ye:
+                rload += 1
+        slot = 0
         rout = ys - K
         for s0 in range(0, nsteps, U):
-            edge = (ys + s0 - K <= 0) or (ys + s0 + U - 1 >= H - 1)
+            edge = (ys + s0 - K <= 0) or (ys + s0 + 2 >= H - 1)
             for ph in range(U):
-                inn = pf[ph % 3].copy()
-                if scale is not None:
-                    inn = F(scale) * inn
-                dv = df[ph % 3].copy()
-                pf[ph % 3] = load(pin, rload); df[ph % 3] = load(div, rload)
+                inn = stage_p[slot].copy(); dv = stage_d[slot].copy()
+                stage_p[slot] = load(pin, rload); stage_d[slot] = load(div, rload)
                 if rload < ye:
                     rload += 1
+                slot = 0 if slot + 1 == D else slot + 1
+                if scale is not None:
+                    inn = F(scale) * inn
                 w[0, (ph + 2) % 3] = inn
-                dr[ph % RD] = dv
+                dr[K + ph] = dv
                 for t in range(1, K + 1):
                     c = w[t - 1, (ph + 1) % 3]
                     below = w[t - 1, (ph + 0) % 3]
@@ -84,7 +89,7 @@ def jacobi_tb_model(pin, div, K, rows_per_chunk, scale=None, row_off=0, out_lo=N
                         r = rout + (K - t)
                         if r == 0: below = c
                         if r == H - 1: above = c
-                    d = dr[(ph - t + RD) % RD]
+                    d = dr[K + ph - t]
                     with np.errstate(invalid="ignore"):
                         o = _jacobi4(below, c, above, d)
                     if t < K:
@@ -93,4 +98,6 @@ def jacobi_tb_model(pin, div, K, rows_per_chunk, scale=None, row_off=0, out_lo=N
                         for l in np.nonzero(lane_out)[0]:
                             pout[rout - row_off, gx[l]:gx[l] + 4] = o[l]
                 rout += 1
+            for j in range(K):
+                dr[j] = dr[j + 3]
     return pout

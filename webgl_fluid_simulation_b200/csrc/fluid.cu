@@ -104,7 +104,7 @@ int launch_tb(fluid_t* h, const JacobiArgs& a) {
     using T = TB<K>;
     const int nxw = (a.W + T::VALID - 1) / T::VALID;
     const int nch = (a.out_hi - a.out_lo + a.rows_per_chunk - 1) / a.rows_per_chunk;
-    jacobi_tb_kernel<K, SCALE><<<nxw * nch, 32, 0, h->stream>>>(a);   // one warp per CTA
+    jacobi_tb_kernel<K, SCALE><<<nxw * nch, 32, T::SMEM, h->stream>>>(a);   // one warp per CTA
     return check_launch(h, "jacobi_tb_kernel");
 }
 
@@ -121,7 +121,7 @@ int tb_rows(const fluid_t* h, int W, int rows) {
     using T = TB<K>;
     const int nxw = (W + T::VALID - 1) / T::VALID;
     int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, jacobi_tb_kernel<K, false>, 32, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, jacobi_tb_kernel<K, false>, 32, T::SMEM);
     if (occ < 1) occ = 1;
     const int resident_warps = h->sm_count * occ;
     const int nch = std::max(1, resident_warps / nxw);

@@ -20,11 +20,10 @@
 //       symmetric in B/T, so rows 0 and H-1 select "below := centre" / "above := centre"
 //       explicitly (EDGE instantiation, only on the few steps that touch those rows);
 //     * div[r] is needed by level t when it produces row r, i.e. K times at K different steps:
-//       each lane keeps its float4 of the last RD rows in a statically indexed register ring
-//       (the step loop is unrolled RD times, so ring slots are compile-time register names);
-//       no shared memory is used at all — the LSU data pipe only carries the shuffles;
-//     * p / div rows are prefetched three steps ahead into registers (coalesced 512 B per warp
-//       row segment, LDG.128).
+//       each lane keeps its float4 of the last K+3 rows in a register ring (see tb_block);
+//     * p / div rows are staged D rows ahead with cp.async (LDGSTS, 16 B per lane, coalesced
+//       512 B per warp row segment) into a per-warp shared-memory ring each lane reads back
+//       itself, so the few resident warps still keep enough bytes in flight for HBM.
 //   The optional SCALE template fuses the clear pass (S:1253-1257, p <- PRESSURE*p) into the
 //   level-0 load of the first launch: one fp32 multiply, same rounding as the separate blit.
 #pragma once
@@ -105,9 +104,28 @@ template <int K>
 struct TB {
     static constexpr int HX = (K + 3) / 4 * 4;       // x halo (columns) on each side of a window
     static constexpr int VALID = 128 - 2 * HX;       // columns a window produces
-    static constexpr int RD = (K + 1 + 2) / 3 * 3;   // div register-ring slots (multiple of 3, > K)
-    static constexpr int U = RD;                     // pipeline steps per unrolled block
+    static constexpr int RD = K + 3;                 // div register-ring slots
+    static constexpr int U = 3;                      // pipeline steps per unrolled block
+    static constexpr int D = 8;                      // staging depth: rows in flight per stream
+    static constexpr int SMEM = D * 2 * 32 * (int)sizeof(float4);   // p + div staging rings
 };
+
+// ---- cp.async (LDGSTS) staging: global -> shared without passing through registers ------------
+// Each lane copies, and later reads back, ONLY its own 16 bytes of a row, so the per-thread
+// completion wait (cp.async.wait_group) is all the synchronisation the ring needs.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ float4 lds128(const float4* p) {
+    float4 v;
+    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
 
 __device__ __forceinline__ float4 rev4(float4 v, bool rev) {
     return rev ? make_float4(v.w, v.z, v.y, v.x) : v;
@@ -160,41 +178,52 @@ __device__ __forceinline__ float4 jacobi4(const float4 below, const float4 c, co
 
 // Per-warp stream state that survives across unrolled blocks.
 struct TBStream {
-    const float4* pl;    // next p row to prefetch (this lane's float4 column group)
-    const float4* dl;    // next div row to prefetch
+    const float4* pl;    // next p row to stage (this lane's float4 column group)
+    const float4* dl;    // next div row to stage
     float4* op;          // where level K's row of THIS step goes (advances one row per step)
+    float4* stage;       // this lane's cell of the staging slot consumed at this step
     int rload;           // global row index pl/dl point at
     int rout;            // global row index op points at  (= ys + s - K)
+    int slot;            // staging slot consumed at this step (0..D-1)
 };
 
-// One unrolled block of U pipeline steps.  All register "rings" are indexed with compile-time
-// constants: the 3-slot p windows rotate with period 3, the div ring dr[RD] with period RD = U,
-// so after one block every value sits in the register it started in and the steady-state loop
-// closes without moves.  (div[r] is consumed by level t when it produces row r, i.e. at K
-// different steps; an earlier version parked it in a shared-memory ring, which made the LSU data
-// pipe — 4 wavefronts per LDS.128 — the bottleneck.  Registers have no such port limit.)
+// One unrolled block of 3 pipeline steps.
+//   * p windows: 3 register slots per level, rotating with period 3 == the unroll, so they are
+//     addressed with compile-time constants and never moved;
+//   * div: level t needs div[r] when it produces row r, i.e. at K different steps.  The last K+3
+//     rows live in the register ring dr[]: the row staged at phase ph sits in dr[K+ph], level t
+//     reads dr[K+ph-t], and the ring is shifted down by 3 at the end of the block (4K MOVs per
+//     3 steps on the otherwise idle ALU pipe).  Earlier variants: a shared-memory ring made the
+//     LSU data pipe the bottleneck (LDS.128 = 4 wavefronts); a move-free ring unrolled RD times
+//     blew the instruction cache.
+//   * p / div rows arrive through a D-deep cp.async staging ring in shared memory: D rows in
+//     flight per stream give the memory-level parallelism the few resident warps cannot.
 // EDGE instantiates the wall selects in y, REV the mirrored-lane reversal in x; both are chosen
 // by warp-uniform branches OUTSIDE the steady-state loop.
 template <int K, bool SCALE, bool EDGE, bool REV>
-__device__ __forceinline__ void tb_block(float4 (&w)[K][3], float4 (&pf)[3], float4 (&df)[3],
-                                         float4 (&dr)[TB<K>::RD], TBStream& st, const int W4,
-                                         const int ye, const int y0, const int y1, const int H,
-                                         const bool rev, const bool lane_out, const float scale) {
+__device__ __forceinline__ void tb_block(float4 (&w)[K][3], float4 (&dr)[TB<K>::RD], TBStream& st,
+                                         float4* __restrict__ ring, const int W4, const int ye,
+                                         const int y0, const int y1, const int H, const bool rev,
+                                         const bool lane_out, const float scale) {
     using T = TB<K>;
 #pragma unroll
-    for (int ph = 0; ph < T::U; ++ph) {
-        // ---- level 0: take the prefetched row, start the prefetch three rows ahead ---------------
-        float4 in = pf[ph % 3];
-        float4 dv = df[ph % 3];
+    for (int ph = 0; ph < 3; ++ph) {
+        // ---- level 0: wait for the oldest staged row, read it, refill its slot --------------------
+        cp_async_wait<T::D - 1>();
+        float4 in = lds128(st.stage);
+        float4 dv = lds128(st.stage + T::D * 32);
+        cp_async16(st.stage, st.pl);
+        cp_async16(st.stage + T::D * 32, st.dl);
+        cp_async_commit();
+        if (st.rload < ye) { ++st.rload; st.pl += W4; st.dl += W4; }   // loads clamp to row ye
+        st.slot = (st.slot + 1 == T::D) ? 0 : st.slot + 1;
+        st.stage = ring + st.slot * 32;
         if (REV) { in = rev4(in, rev); dv = rev4(dv, rev); }
         if (SCALE) {
             in.x = scale * in.x; in.y = scale * in.y; in.z = scale * in.z; in.w = scale * in.w;
         }
-        pf[ph % 3] = __ldg(st.pl);
-        df[ph % 3] = __ldg(st.dl);
-        if (st.rload < ye) { ++st.rload; st.pl += W4; st.dl += W4; }   // loads clamp to row ye
         w[0][(ph + 2) % 3] = in;
-        dr[ph % T::RD] = dv;
+        dr[K + ph] = dv;
         // ---- levels 1..K ------------------------------------------------------------------------
 #pragma unroll
         for (int t = 1; t <= K; ++t) {
@@ -206,7 +235,7 @@ __device__ __forceinline__ void tb_block(float4 (&w)[K][3], float4 (&pf)[3], flo
                 if (r == 0) below = c;            // CLAMP_TO_EDGE: p[i,-1] = p[i,0]
                 if (r == H - 1) above = c;        //                p[i,H]  = p[i,H-1]
             }
-            const float4 d = dr[(ph - t + T::RD) % T::RD];   // div row loaded t steps ago
+            const float4 d = dr[K + ph - t];      // div row staged t steps ago
             const float4 o = jacobi4(below, c, above, d);
             if (t < K) {
                 w[t][(ph + 2) % 3] = o;
@@ -217,11 +246,14 @@ __device__ __forceinline__ void tb_block(float4 (&w)[K][3], float4 (&pf)[3], flo
         ++st.rout;
         st.op += W4;
     }
+#pragma unroll
+    for (int j = 0; j < K; ++j) dr[j] = dr[j + 3];
 }
 
 template <int K, bool SCALE, bool REV>
-__device__ __forceinline__ void tb_stream(const JacobiArgs& a, const int lc, const int gx,
-                                          const bool rev, const bool lane_out, const int cy) {
+__device__ __forceinline__ void tb_stream(const JacobiArgs& a, float4* __restrict__ ring,
+                                          const int lc, const int gx, const bool rev,
+                                          const bool lane_out, const int cy) {
     using T = TB<K>;
     const int W = a.W, H = a.H, W4 = W >> 2;
     // ---- y geometry of this warp's stream ----------------------------------------------------------
@@ -246,35 +278,38 @@ __device__ __forceinline__ void tb_stream(const JacobiArgs& a, const int lc, con
 #pragma unroll
     for (int q = 0; q < T::RD; ++q) dr[q] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    // prefetch buffers, three rows ahead
-    float4 pf[3], df[3];
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {
-        const int r = min(ys + q, ye);
-        pf[q] = __ldg(Pg + (ptrdiff_t)r * W4);
-        df[q] = __ldg(Dg + (ptrdiff_t)r * W4);
-    }
+    // fill the staging ring: rows ys .. ys+D-1 (clamped to ye), one cp.async group per row
     TBStream st;
-    st.rload = min(ys + 3, ye);
-    st.pl = Pg + (ptrdiff_t)st.rload * W4;
-    st.dl = Dg + (ptrdiff_t)st.rload * W4;
+    st.rload = ys;
+    st.pl = Pg + (ptrdiff_t)ys * W4;
+    st.dl = Dg + (ptrdiff_t)ys * W4;
+#pragma unroll
+    for (int q = 0; q < T::D; ++q) {
+        cp_async16(ring + q * 32, st.pl);
+        cp_async16(ring + (T::D + q) * 32, st.dl);
+        cp_async_commit();
+        if (st.rload < ye) { ++st.rload; st.pl += W4; st.dl += W4; }
+    }
+    st.slot = 0;
+    st.stage = ring;
     st.rout = ys - K;
     st.op = Og + (ptrdiff_t)st.rout * W4;             // only dereferenced for rows in [y0, y1)
 
-    // A block touches a wall row when its rows [ys+s0-K, ys+s0+U-1] reach row 0 or row H-1: the
+    // A block touches a wall row when its rows [ys+s0-K, ys+s0+2] reach row 0 or row H-1: the
     // first blocks of a bottom chunk and the last ones of a top chunk.  Wall and steady-state
     // blocks run in SEPARATE loops (not one loop with a branch) so that the steady-state loop
-    // has its own register assignment and its rotations close without a single MOV.
+    // has its own register assignment and its window rotation closes without moves.
     int s0 = 0;
 #pragma unroll 1
     for (int part = 0; part < 2; ++part) {
 #pragma unroll 1
-        for (; s0 < nsteps && ((ys + s0 - K <= 0) || (ys + s0 + T::U - 1 >= H - 1)); s0 += T::U)
-            tb_block<K, SCALE, true, REV>(w, pf, df, dr, st, W4, ye, y0, y1, H, rev, lane_out, a.scale);
+        for (; s0 < nsteps && ((ys + s0 - K <= 0) || (ys + s0 + 2 >= H - 1)); s0 += 3)
+            tb_block<K, SCALE, true, REV>(w, dr, st, ring, W4, ye, y0, y1, H, rev, lane_out, a.scale);
 #pragma unroll 1
-        for (; s0 < nsteps && !((ys + s0 - K <= 0) || (ys + s0 + T::U - 1 >= H - 1)); s0 += T::U)
-            tb_block<K, SCALE, false, REV>(w, pf, df, dr, st, W4, ye, y0, y1, H, rev, lane_out, a.scale);
+        for (; s0 < nsteps && !((ys + s0 - K <= 0) || (ys + s0 + 2 >= H - 1)); s0 += 3)
+            tb_block<K, SCALE, false, REV>(w, dr, st, ring, W4, ye, y0, y1, H, rev, lane_out, a.scale);
     }
+    cp_async_wait<0>();                               // drain the over-fetched tail before exit
 }
 
 // One warp per CTA: every quantity that steers control flow derives from blockIdx and kernel
@@ -283,6 +318,7 @@ __device__ __forceinline__ void tb_stream(const JacobiArgs& a, const int lc, con
 template <int K, bool SCALE>
 __global__ void __launch_bounds__(32) jacobi_tb_kernel(JacobiArgs a) {
     using T = TB<K>;
+    extern __shared__ float4 smem4[];
     const int lane = threadIdx.x;
     const int nxw = (a.W + T::VALID - 1) / T::VALID;
     const int wid = blockIdx.x;
@@ -298,8 +334,9 @@ __global__ void __launch_bounds__(32) jacobi_tb_kernel(JacobiArgs a) {
     lc = min(max(lc, 0), W - 4);
     const bool any_rev = (wx == 0) || ((wx + 1) * T::VALID + T::HX > W);   // warp-uniform
     const bool lane_out = (lane >= T::HX / 4) && (lane < 32 - T::HX / 4) && (gx >= 0) && (gx < W);
-    if (any_rev) tb_stream<K, SCALE, true>(a, lc, gx, rev, lane_out, cy);
-    else tb_stream<K, SCALE, false>(a, lc, gx, rev, lane_out, cy);
+    float4* ring = smem4 + lane;                      // p slot q at ring[q*32], div at ring[(D+q)*32]
+    if (any_rev) tb_stream<K, SCALE, true>(a, ring, lc, gx, rev, lane_out, cy);
+    else tb_stream<K, SCALE, false>(a, ring, lc, gx, rev, lane_out, cy);
 }
 
 }  // namespace fk
