@@ -155,7 +155,7 @@ int run_jacobi(fluid_t* h, int iters, bool scale_first, int* launches_out) {
     JacobiArgs a{};
     a.div = h->divergence; a.W = W; a.H = H; a.row_off = 0; a.out_lo = h->row0; a.out_hi = h->row1;
     a.scale = h->cfg.pressure;
-    int kb = h->cfg.jacobi_block > 0 ? h->cfg.jacobi_block : 8;
+    int kb = h->cfg.jacobi_block > 0 ? h->cfg.jacobi_block : 10;  // tuned on B200: profiles/r01_tune_jacobi.txt
     kb = std::min(kb, KMAX);
     const bool naive = (h->cfg.flags & FLUID_FLAG_NAIVE_JACOBI) || kb == 1;
     if (iters <= 0) {
