@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "jacobi.cuh"
+#include "nccl_dl.h"
 #include "passes.cuh"
 
 namespace {
@@ -50,9 +51,17 @@ struct fluid {
     std::string err;
     int jacobi_rows_override = 0;    // FLUID_JACOBI_ROWS env (tuning)
 
-    // single GPU: the slab is the whole grid
-    int row0 = 0, row1 = 0;          // owned sim rows
-    int drow0 = 0, drow1 = 0;        // owned dye rows
+    // ---- row-slab decomposition.  Single GPU: rank 0 of 1, no ghost rows. -------------
+    int rank = 0, world = 1;
+    int G = 0, Gd = 0;               // ghost rows kept below and above the owned rows (sim / dye)
+    int row0 = 0, row1 = 0;          // owned sim rows  [row0, row1)
+    int drow0 = 0, drow1 = 0;        // owned dye rows  [drow0, drow1)
+    int roff = 0, droff = 0;         // global row index of local row 0  (row0 - G, drow0 - Gd)
+    ncdl::ncclComm_t comm = nullptr;
+    bool v_ghost_valid = true;       // velocity valid on owned rows +-3 (what the next step needs)
+    bool slab() const { return world > 1; }
+    int lrows() const { return row1 - row0 + 2 * G; }
+    int ldrows() const { return drow1 - drow0 + 2 * Gd; }
 };
 
 namespace {
@@ -81,17 +90,49 @@ inline dim3 grid2d(int W, int rows, dim3 b) {
     return dim3((W + b.x - 1) / b.x, (rows + b.y - 1) / b.y);
 }
 
-Grid sim_grid(const fluid_t* h) { return Grid{h->cfg.sim_w, h->cfg.sim_h, 0, h->row0, h->row1}; }
-Grid dye_grid(const fluid_t* h) { return Grid{h->cfg.dye_w, h->cfg.dye_h, 0, h->drow0, h->drow1}; }
+Grid sim_grid(const fluid_t* h) { return Grid{h->cfg.sim_w, h->cfg.sim_h, h->roff, h->row0, h->row1}; }
+Grid dye_grid(const fluid_t* h) { return Grid{h->cfg.dye_w, h->cfg.dye_h, h->droff, h->drow0, h->drow1}; }
+// same grid, producing rows [row0-e, row1+e) clipped to the domain (redundant ghost-zone compute)
+Grid sim_grid_ext(const fluid_t* h, int e) {
+    Grid g = sim_grid(h);
+    g.j_lo = std::max(h->row0 - e, 0); g.j_hi = std::min(h->row1 + e, h->cfg.sim_h);
+    return g;
+}
 
-size_t sim_cells(const fluid_t* h) { return (size_t)h->cfg.sim_w * h->cfg.sim_h; }
-size_t dye_cells(const fluid_t* h) { return (size_t)h->cfg.dye_w * h->cfg.dye_h; }
+// LOCAL cell counts (owned + ghost rows): what the device buffers hold
+size_t sim_cells(const fluid_t* h) { return (size_t)h->cfg.sim_w * h->lrows(); }
+size_t dye_cells(const fluid_t* h) { return (size_t)h->cfg.dye_w * h->ldrows(); }
 
 int check_launch(fluid_t* h, const char* what, int n = 1) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess)
         return fail(h, FLUID_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
     h->launches += n;
+    return FLUID_OK;
+}
+
+// ---- halo exchange (NCCL point-to-point, both neighbours in one group) -----------------------------
+// Sends my top `n` owned rows up and my bottom `n` owned rows down; receives the neighbours' rows
+// into my ghost rows.  `base` is local row 0 of a buffer whose local row 0 is global row `off`.
+int exchange_rows(fluid_t* h, void* base, size_t row_bytes, int off, int r0, int r1, int n) {
+    if (!h->slab() || n <= 0) return FLUID_OK;
+    if (n > r1 - r0)
+        return fail(h, FLUID_ERR_HALO, "halo of %d rows exceeds the slab height %d (use fewer GPUs or a taller grid)", n, r1 - r0);
+    ncdl::Api& N = ncdl::api();
+    char* b = static_cast<char*>(base);
+    auto at = [&](int grow) { return b + (size_t)(grow - off) * row_bytes; };
+    const size_t bytes = (size_t)n * row_bytes;
+    int rc = N.GroupStart();
+    if (h->rank + 1 < h->world) {
+        if (!rc) rc = N.Send(at(r1 - n), bytes, ncdl::ncclInt8, h->rank + 1, h->comm, h->stream);
+        if (!rc) rc = N.Recv(at(r1), bytes, ncdl::ncclInt8, h->rank + 1, h->comm, h->stream);
+    }
+    if (h->rank > 0) {
+        if (!rc) rc = N.Send(at(r0), bytes, ncdl::ncclInt8, h->rank - 1, h->comm, h->stream);
+        if (!rc) rc = N.Recv(at(r0 - n), bytes, ncdl::ncclInt8, h->rank - 1, h->comm, h->stream);
+    }
+    const int rc2 = N.GroupEnd();
+    if (rc || rc2) return fail(h, FLUID_ERR_NCCL, "NCCL halo exchange failed: %s", N.GetErrorString(rc ? rc : rc2));
     return FLUID_OK;
 }
 
@@ -149,17 +190,21 @@ bool tb_eligible(const fluid_t* h) {
 
 // `iters` sweeps reading pressure.read, result in pressure.read (swaps like S:1265).
 // scale_first: fold p <- PRESSURE*p (clear pass) into the first sweep's loads.
+// On a slab: before a launch of depth K the neighbours' K rows of p are exchanged (K+1 for the last
+// launch, which also produces one row beyond each slab edge so that gradientSubtract needs no
+// message of its own); divergence ghosts are exchanged once per solve (it is constant in the loop).
 int run_jacobi(fluid_t* h, int iters, bool scale_first, int* launches_out) {
     int nl = 0;
     const int W = h->cfg.sim_w, H = h->cfg.sim_h;
     JacobiArgs a{};
-    a.div = h->divergence; a.W = W; a.H = H; a.row_off = 0; a.out_lo = h->row0; a.out_hi = h->row1;
+    a.div = h->divergence; a.W = W; a.H = H; a.row_off = h->roff; a.out_lo = h->row0; a.out_hi = h->row1;
     a.scale = h->cfg.pressure;
     int kb = h->cfg.jacobi_block > 0 ? h->cfg.jacobi_block : 10;  // tuned on B200: profiles/r01_tune_jacobi.txt
     kb = std::min(kb, KMAX);
+    if (h->slab()) kb = std::min(kb, h->G - 1);
     const bool naive = (h->cfg.flags & FLUID_FLAG_NAIVE_JACOBI) || kb == 1;
     if (iters <= 0) {
-        if (scale_first) {   // clear pass alone
+        if (scale_first) {   // clear pass alone (owned + ghost rows; ghosts are refreshed before use anyway)
             const size_t n = sim_cells(h);
             scale_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(
                 (const float*)h->pressure.read, (float*)h->pressure.write, n, h->cfg.pressure);
@@ -169,34 +214,42 @@ int run_jacobi(fluid_t* h, int iters, bool scale_first, int* launches_out) {
         if (launches_out) *launches_out = nl;
         return FLUID_OK;
     }
-    if (!tb_eligible(h)) {
-        dim3 b(64, 4);
-        for (int k = 0; k < iters; ++k) {
-            a.pin = (const float*)h->pressure.read; a.pout = (float*)h->pressure.write;
-            jacobi_scalar_kernel<<<grid2d(W, a.out_hi - a.out_lo, b), b, 0, h->stream>>>(
-                a, scale_first && k == 0);
-            int rc = check_launch(h, "jacobi_scalar_kernel"); if (rc) return rc;
-            h->pressure.swap(); ++nl;
+    const bool blocked = tb_eligible(h) && !naive;
+    const int nlaunch = blocked ? (iters + kb - 1) / kb : iters;
+    const int base = iters / nlaunch, extra = iters % nlaunch;
+    if (h->slab()) {   // divergence ghost rows: the deepest launch needs kmax rows (incl. the +1 extension)
+        const int kmax = base + (extra ? 1 : 0);
+        int rc = exchange_rows(h, h->divergence, (size_t)W * sizeof(float), h->roff, h->row0, h->row1, kmax);
+        if (rc) return rc;
+    }
+    for (int k = 0; k < nlaunch; ++k) {
+        const int K = base + (k < extra ? 1 : 0);
+        const bool last = (k == nlaunch - 1);
+        a.pin = (const float*)h->pressure.read; a.pout = (float*)h->pressure.write;
+        a.out_lo = h->row0; a.out_hi = h->row1;
+        if (h->slab()) {
+            const int ext = last ? 1 : 0;
+            int rc = exchange_rows(h, h->pressure.read, (size_t)W * sizeof(float), h->roff, h->row0, h->row1, K + ext);
+            if (rc) return rc;
+            a.out_lo = std::max(h->row0 - ext, 0); a.out_hi = std::min(h->row1 + ext, H);
         }
-    } else if (naive) {
-        dim3 b(32, 8);
-        for (int k = 0; k < iters; ++k) {
-            a.pin = (const float*)h->pressure.read; a.pout = (float*)h->pressure.write;
+        const bool sc = scale_first && k == 0;
+        int rc;
+        if (blocked) {
+            rc = launch_tb_dyn(h, K, a, sc);
+        } else if (tb_eligible(h)) {
+            dim3 b(32, 8);
             dim3 g((W / 4 + b.x - 1) / b.x, (a.out_hi - a.out_lo + b.y - 1) / b.y);
-            if (scale_first && k == 0) jacobi_sweep_kernel<true><<<g, b, 0, h->stream>>>(a);
+            if (sc) jacobi_sweep_kernel<true><<<g, b, 0, h->stream>>>(a);
             else jacobi_sweep_kernel<false><<<g, b, 0, h->stream>>>(a);
-            int rc = check_launch(h, "jacobi_sweep_kernel"); if (rc) return rc;
-            h->pressure.swap(); ++nl;
+            rc = check_launch(h, "jacobi_sweep_kernel");
+        } else {
+            dim3 b(64, 4);
+            jacobi_scalar_kernel<<<grid2d(W, a.out_hi - a.out_lo, b), b, 0, h->stream>>>(a, sc);
+            rc = check_launch(h, "jacobi_scalar_kernel");
         }
-    } else {
-        // balanced split of `iters` into ceil(iters/kb) launches of depth <= kb
-        const int n = (iters + kb - 1) / kb, base = iters / n, extra = iters % n;
-        for (int k = 0; k < n; ++k) {
-            const int K = base + (k < extra ? 1 : 0);
-            a.pin = (const float*)h->pressure.read; a.pout = (float*)h->pressure.write;
-            int rc = launch_tb_dyn(h, K, a, scale_first && k == 0); if (rc) return rc;
-            h->pressure.swap(); ++nl;
-        }
+        if (rc) return rc;
+        h->pressure.swap(); ++nl;
     }
     if (launches_out) *launches_out = nl;
     return FLUID_OK;
@@ -232,18 +285,104 @@ void free_fields(fluid_t* h) {
     h->divergence = h->curl = nullptr;
 }
 
+// pointer to the first OWNED row of a field's .read buffer, plus its owned extent
 int field_info(const fluid_t* h, int field, void** ptr, int* w, int* rows, int* ch) {
+    const size_t so = (size_t)h->G * h->cfg.sim_w, doff_ = (size_t)h->Gd * h->cfg.dye_w;
     switch (field) {
-        case FLUID_FIELD_VELOCITY: *ptr = h->velocity.read; *w = h->cfg.sim_w; *rows = h->row1 - h->row0; *ch = 2; return 0;
-        case FLUID_FIELD_DYE: *ptr = h->dye.read; *w = h->cfg.dye_w; *rows = h->drow1 - h->drow0; *ch = 4; return 0;
-        case FLUID_FIELD_PRESSURE: *ptr = h->pressure.read; *w = h->cfg.sim_w; *rows = h->row1 - h->row0; *ch = 1; return 0;
-        case FLUID_FIELD_DIVERGENCE: *ptr = h->divergence; *w = h->cfg.sim_w; *rows = h->row1 - h->row0; *ch = 1; return 0;
-        case FLUID_FIELD_CURL: *ptr = h->curl; *w = h->cfg.sim_w; *rows = h->row1 - h->row0; *ch = 1; return 0;
+        case FLUID_FIELD_VELOCITY: *ptr = (float2*)h->velocity.read + so; *w = h->cfg.sim_w; *rows = h->row1 - h->row0; *ch = 2; return 0;
+        case FLUID_FIELD_DYE: *ptr = (float4*)h->dye.read + doff_; *w = h->cfg.dye_w; *rows = h->drow1 - h->drow0; *ch = 4; return 0;
+        case FLUID_FIELD_PRESSURE: *ptr = (float*)h->pressure.read + so; *w = h->cfg.sim_w; *rows = h->row1 - h->row0; *ch = 1; return 0;
+        case FLUID_FIELD_DIVERGENCE: *ptr = h->divergence + so; *w = h->cfg.sim_w; *rows = h->row1 - h->row0; *ch = 1; return 0;
+        case FLUID_FIELD_CURL: *ptr = h->curl + so; *w = h->cfg.sim_w; *rows = h->row1 - h->row0; *ch = 1; return 0;
     }
     return -1;
 }
 
-int check_halo(fluid_t* h) { (void)h; return FLUID_OK; }  // single GPU: taps are always clamped in-grid
+// Multi-GPU: an advection back-trace that needed a row outside the ghost zone set the device flag;
+// never clamp silently — report it at the next synchronisation point.
+int check_halo(fluid_t* h) {
+    if (!h->slab()) return FLUID_OK;   // single GPU: taps are always clamped in-grid
+    int flag = 0;
+    CU(cudaMemcpyAsync(&flag, h->halo_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (flag)
+        return fail(h, FLUID_ERR_HALO, "advection back-trace left the %d-row ghost zone: |v|*dt exceeds it; "
+                    "re-create the slab handle with a taller halo (FLUID_HALO_ROWS)", h->G);
+    return FLUID_OK;
+}
+
+int not_on_slab(fluid_t* h, const char* what) {
+    return fail(h, FLUID_ERR_INVALID, "%s is a single-GPU test entry point; a slab handle supports "
+                "fluid_step / fluid_splat / fluid_pass_pressure_solve / fluid_pass_jacobi / read / write", what);
+}
+
+// shared by fluid_create and fluid_create_slab
+int create_common(const fluid_config* cfg, int rank, int world, const void* uid, fluid_t** out) {
+    fluid_t* h = nullptr;
+    if (!cfg || !out) return fail(h, FLUID_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->sim_w < 1 || cfg->sim_h < 1 || cfg->dye_w < 1 || cfg->dye_h < 1)
+        return fail(h, FLUID_ERR_INVALID, "bad resolution %dx%d / %dx%d", cfg->sim_w, cfg->sim_h,
+                    cfg->dye_w, cfg->dye_h);
+    if (world < 1 || rank < 0 || rank >= world) return fail(h, FLUID_ERR_INVALID, "bad rank %d of %d", rank, world);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(h, FLUID_ERR_NO_DEVICE, "no CUDA device: libfluid_b200 has no CPU path");
+    }
+    int dev = cfg->device;
+    if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) dev = 0; }
+    if (dev >= ndev) return fail(h, FLUID_ERR_INVALID, "device %d of %d", dev, ndev);
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess || prop.major != 10)
+        return fail(h, FLUID_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only",
+                    dev, prop.major, prop.minor);
+    if (cudaSetDevice(dev) != cudaSuccess) return fail(h, FLUID_ERR_CUDA, "cudaSetDevice(%d)", dev);
+
+    h = new fluid();
+    h->cfg = *cfg;
+    h->device = dev;
+    h->sm_count = prop.multiProcessorCount;
+    if (!(h->cfg.aspect > 0.0f)) h->cfg.aspect = (float)((double)cfg->sim_w / (double)cfg->sim_h);
+    h->rank = rank; h->world = world;
+    const int H = cfg->sim_h, Hd = cfg->dye_h;
+    h->row0 = (int)((long long)H * rank / world);  h->row1 = (int)((long long)H * (rank + 1) / world);
+    h->drow0 = (int)((long long)Hd * rank / world); h->drow1 = (int)((long long)Hd * (rank + 1) / world);
+    if (world > 1) {
+        int g = 32;                                   // rows: 3 (ghost compute) + dt*|v|max + 2, see DESIGN.md
+        if (const char* e = getenv("FLUID_HALO_ROWS")) g = std::max(14, atoi(e));
+        h->G = g;
+        h->Gd = g * std::max(1, (Hd + H - 1) / H);   // same physical reach on the dye grid
+        if (h->row1 - h->row0 < h->G || h->drow1 - h->drow0 < h->Gd) {
+            int rc = fail(nullptr, FLUID_ERR_INVALID, "slab of %d rows is shorter than the %d-row halo", h->row1 - h->row0, h->G);
+            delete h; return rc;
+        }
+    }
+    h->roff = h->row0 - h->G; h->droff = h->drow0 - h->Gd;
+    if (const char* e = getenv("FLUID_JACOBI_ROWS")) h->jacobi_rows_override = atoi(e);
+    auto body = [&]() -> int {
+        CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        for (auto& e : h->mark) CU(cudaEventCreate(&e));
+        for (auto& e : h->tev) CU(cudaEventCreate(&e));
+        CU(cudaMalloc((void**)&h->halo_flag, sizeof(int)));
+        CU(cudaMemsetAsync(h->halo_flag, 0, sizeof(int), h->stream));
+        int r = alloc_fields(h); if (r) return r;
+        CU(cudaStreamSynchronize(h->stream));
+        if (world > 1) {
+            ncdl::Api& N = ncdl::api();
+            if (!N.handle) return fail(h, FLUID_ERR_NCCL, "NCCL not available: %s", N.why);
+            ncdl::ncclUniqueId id;
+            memcpy(&id, uid, sizeof id);
+            int rc = N.CommInitRank(&h->comm, world, id, rank);
+            if (rc) return fail(h, FLUID_ERR_NCCL, "ncclCommInitRank failed: %s", N.GetErrorString(rc));
+        }
+        return FLUID_OK;
+    };
+    int rc = body();
+    if (rc != FLUID_OK) { g_create_error = h->err; fluid_destroy(h); return rc; }
+    *out = h;
+    return FLUID_OK;
+}
 
 }  // namespace
 
@@ -281,61 +420,24 @@ void fluid_get_resolution(int resolution, int canvas_w, int canvas_h, int* out_w
 
 const char* fluid_last_error(fluid_t* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
-int fluid_create(const fluid_config* cfg, fluid_t** out) {
-    fluid_t* h = nullptr;
-    if (!cfg || !out) return fail(h, FLUID_ERR_INVALID, "null argument");
-    *out = nullptr;
-    if (cfg->sim_w < 1 || cfg->sim_h < 1 || cfg->dye_w < 1 || cfg->dye_h < 1)
-        return fail(h, FLUID_ERR_INVALID, "bad resolution %dx%d / %dx%d", cfg->sim_w, cfg->sim_h,
-                    cfg->dye_w, cfg->dye_h);
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-        cudaGetLastError();
-        return fail(h, FLUID_ERR_NO_DEVICE, "no CUDA device: libfluid_b200 has no CPU path");
-    }
-    int dev = cfg->device;
-    if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) dev = 0; }
-    if (dev >= ndev) return fail(h, FLUID_ERR_INVALID, "device %d of %d", dev, ndev);
-    cudaDeviceProp prop{};
-    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess || prop.major != 10)
-        return fail(h, FLUID_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only",
-                    dev, prop.major, prop.minor);
-    if (cudaSetDevice(dev) != cudaSuccess) return fail(h, FLUID_ERR_CUDA, "cudaSetDevice(%d)", dev);
-
-    h = new fluid();
-    h->cfg = *cfg;
-    h->device = dev;
-    h->sm_count = prop.multiProcessorCount;
-    if (!(h->cfg.aspect > 0.0f)) h->cfg.aspect = (float)((double)cfg->sim_w / (double)cfg->sim_h);
-    h->row0 = 0; h->row1 = cfg->sim_h; h->drow0 = 0; h->drow1 = cfg->dye_h;
-    if (const char* e = getenv("FLUID_JACOBI_ROWS")) h->jacobi_rows_override = atoi(e);
-    int rc = FLUID_OK;
-    auto body = [&]() -> int {
-        CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-        for (auto& e : h->mark) CU(cudaEventCreate(&e));
-        for (auto& e : h->tev) CU(cudaEventCreate(&e));
-        CU(cudaMalloc((void**)&h->halo_flag, sizeof(int)));
-        CU(cudaMemsetAsync(h->halo_flag, 0, sizeof(int), h->stream));
-        int r = alloc_fields(h); if (r) return r;
-        CU(cudaStreamSynchronize(h->stream));
-        return FLUID_OK;
-    };
-    rc = body();
-    if (rc != FLUID_OK) { g_create_error = h->err; fluid_destroy(h); return rc; }
-    *out = h;
-    return FLUID_OK;
-}
+int fluid_create(const fluid_config* cfg, fluid_t** out) { return create_common(cfg, 0, 1, nullptr, out); }
 
 int fluid_nccl_unique_id(void* out_uid, size_t uid_bytes) {
-    (void)out_uid; (void)uid_bytes;
-    return fail(nullptr, FLUID_ERR_NCCL, "multi-GPU slabs are not built into this library yet");
+    if (!out_uid || uid_bytes < sizeof(ncdl::ncclUniqueId)) return fail(nullptr, FLUID_ERR_INVALID, "uid buffer must hold 128 bytes");
+    ncdl::Api& N = ncdl::api();
+    if (!N.handle) return fail(nullptr, FLUID_ERR_NCCL, "NCCL not available: %s", N.why);
+    ncdl::ncclUniqueId id;
+    int rc = N.GetUniqueId(&id);
+    if (rc) return fail(nullptr, FLUID_ERR_NCCL, "ncclGetUniqueId failed: %s", N.GetErrorString(rc));
+    memcpy(out_uid, &id, sizeof id);
+    return FLUID_OK;
 }
 
 int fluid_create_slab(const fluid_config* cfg, int rank, int world, const void* nccl_uid,
                       size_t uid_bytes, fluid_t** out) {
-    (void)nccl_uid; (void)uid_bytes;
-    if (world == 1 && rank == 0) return fluid_create(cfg, out);
-    return fail(nullptr, FLUID_ERR_NCCL, "multi-GPU slabs are not built into this library yet");
+    if (world > 1 && (!nccl_uid || uid_bytes < sizeof(ncdl::ncclUniqueId)))
+        return fail(nullptr, FLUID_ERR_INVALID, "nccl_uid must be the 128 bytes from fluid_nccl_unique_id()");
+    return create_common(cfg, rank, world, nccl_uid, out);
 }
 
 void fluid_destroy(fluid_t* h) {
@@ -344,6 +446,7 @@ void fluid_destroy(fluid_t* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     free_fields(h);
     cudaFree(h->halo_flag);
+    if (h->comm) { ncdl::api().CommDestroy(h->comm); h->comm = nullptr; }
     if (h->pin_a) cudaFreeHost(h->pin_a);
     if (h->pin_b) cudaFreeHost(h->pin_b);
     for (auto& e : h->mark) if (e) cudaEventDestroy(e);
@@ -385,36 +488,29 @@ int fluid_get_param(fluid_t* h, int key, float* v) {
 }
 
 // ---- passes ---------------------------------------------------------------------------------------
+// do_*: launch on an explicit row range (owned rows, or owned +- e for redundant ghost compute on a
+// slab); the public fluid_pass_* wrappers are the single-GPU, one-blit-per-call test surface.
 
-int fluid_pass_curl(fluid_t* h) {
-    if (!h) return FLUID_ERR_INVALID;
-    dim3 b(64, 4); Grid g = sim_grid(h);
-    curl_kernel<<<grid2d(g.W, g.j_hi - g.j_lo, b), b, 0, h->stream>>>((const float2*)h->velocity.read,
-                                                                     h->curl, g);
+static int do_curl(fluid_t* h, Grid g) {
+    dim3 b(64, 4);
+    curl_kernel<<<grid2d(g.W, g.j_hi - g.j_lo, b), b, 0, h->stream>>>((const float2*)h->velocity.read, h->curl, g);
     return check_launch(h, "curl_kernel");
 }
-
-int fluid_pass_vorticity(fluid_t* h, float dt) {
-    if (!h) return FLUID_ERR_INVALID;
-    dim3 b(64, 4); Grid g = sim_grid(h);
+static int do_vorticity(fluid_t* h, Grid g, float dt) {
+    dim3 b(64, 4);
     vorticity_kernel<<<grid2d(g.W, g.j_hi - g.j_lo, b), b, 0, h->stream>>>(
         (const float2*)h->velocity.read, h->curl, (float2*)h->velocity.write, g, h->cfg.curl, dt);
     int rc = check_launch(h, "vorticity_kernel"); if (rc) return rc;
     h->velocity.swap();                                   // S:1246
     return FLUID_OK;
 }
-
-int fluid_pass_divergence(fluid_t* h) {
-    if (!h) return FLUID_ERR_INVALID;
-    dim3 b(64, 4); Grid g = sim_grid(h);
+static int do_divergence(fluid_t* h, Grid g) {
+    dim3 b(64, 4);
     divergence_kernel<<<grid2d(g.W, g.j_hi - g.j_lo, b), b, 0, h->stream>>>(
         (const float2*)h->velocity.read, h->divergence, g);
     return check_launch(h, "divergence_kernel");
 }
-
-int fluid_pass_curl_vorticity_divergence(fluid_t* h, float dt) {
-    if (!h) return FLUID_ERR_INVALID;
-    Grid g = sim_grid(h);
+static int do_cvd(fluid_t* h, Grid g, float dt) {
     dim3 b(64, 4);
     dim3 grid((g.W + CVD_TX - 1) / CVD_TX, (g.j_hi - g.j_lo + CVD_TY - 1) / CVD_TY);
     curl_vorticity_divergence_kernel<<<grid, b, 0, h->stream>>>(
@@ -424,53 +520,38 @@ int fluid_pass_curl_vorticity_divergence(fluid_t* h, float dt) {
     h->velocity.swap();
     return FLUID_OK;
 }
-
-int fluid_pass_clear_pressure(fluid_t* h) {
-    if (!h) return FLUID_ERR_INVALID;
-    return run_jacobi(h, 0, true, nullptr);
-}
-
-int fluid_pass_jacobi(fluid_t* h, int iters) {
-    if (!h) return FLUID_ERR_INVALID;
-    if (iters < 0) return fail(h, FLUID_ERR_INVALID, "iters < 0");
-    return run_jacobi(h, iters, false, nullptr);
-}
-
-int fluid_pass_pressure_solve(fluid_t* h) {
-    if (!h) return FLUID_ERR_INVALID;
-    return run_jacobi(h, h->cfg.pressure_iterations, true, nullptr);
-}
-
-int fluid_pass_gradient_subtract(fluid_t* h) {
-    if (!h) return FLUID_ERR_INVALID;
-    dim3 b(64, 4); Grid g = sim_grid(h);
+static int do_gradient(fluid_t* h, Grid g) {
+    dim3 b(64, 4);
     gradient_subtract_kernel<<<grid2d(g.W, g.j_hi - g.j_lo, b), b, 0, h->stream>>>(
         (const float*)h->pressure.read, (const float2*)h->velocity.read, (float2*)h->velocity.write, g);
     int rc = check_launch(h, "gradient_subtract_kernel"); if (rc) return rc;
     h->velocity.swap();                                   // S:1273
     return FLUID_OK;
 }
-
-int fluid_pass_advect_velocity(fluid_t* h, float dt) {
-    if (!h) return FLUID_ERR_INVALID;
+// valid source rows of a slab buffer: owned + ghost, clipped to the domain
+static void valid_rows(int r0, int r1, int g, int H, int* lo, int* hi) {
+    *lo = std::max(r0 - g, 0); *hi = std::min(r1 + g, H);
+}
+static int do_advect_velocity(fluid_t* h, Grid out, float dt) {
     dim3 b(64, 4);
     AdvectArgs a{};
-    a.vel = sim_grid(h); a.src = sim_grid(h);
-    a.vel_lo = 0; a.vel_hi = h->cfg.sim_h; a.src_lo = 0; a.src_hi = h->cfg.sim_h;
+    a.vel = sim_grid(h); a.src = out;
+    valid_rows(h->row0, h->row1, h->G, h->cfg.sim_h, &a.vel_lo, &a.vel_hi);
+    a.src_lo = a.vel_lo; a.src_hi = a.vel_hi;
     a.dt = dt; a.dissipation = h->cfg.velocity_dissipation; a.halo_violation = h->halo_flag;
-    advect_velocity_kernel<<<grid2d(a.src.W, a.src.j_hi - a.src.j_lo, b), b, 0, h->stream>>>(
+    advect_velocity_kernel<<<grid2d(out.W, out.j_hi - out.j_lo, b), b, 0, h->stream>>>(
         (const float2*)h->velocity.read, (float2*)h->velocity.write, a);
     int rc = check_launch(h, "advect_velocity_kernel"); if (rc) return rc;
     h->velocity.swap();                                   // S:1285
     return FLUID_OK;
 }
-
-int fluid_pass_advect_dye(fluid_t* h, float dt) {
-    if (!h) return FLUID_ERR_INVALID;
+static int do_advect_dye(fluid_t* h, float dt) {
     dim3 b(64, 4);
     AdvectArgs a{};
     a.vel = sim_grid(h); a.src = dye_grid(h);
-    a.vel_lo = 0; a.vel_hi = h->cfg.sim_h; a.src_lo = 0; a.src_hi = h->cfg.dye_h;
+    // after the velocity advection the slab holds valid velocity on owned rows +- 3
+    valid_rows(h->row0, h->row1, h->slab() ? 3 : 0, h->cfg.sim_h, &a.vel_lo, &a.vel_hi);
+    valid_rows(h->drow0, h->drow1, h->Gd, h->cfg.dye_h, &a.src_lo, &a.src_hi);
     a.dt = dt; a.dissipation = h->cfg.density_dissipation; a.halo_violation = h->halo_flag;
     advect_dye_kernel<<<grid2d(a.src.W, a.src.j_hi - a.src.j_lo, b), b, 0, h->stream>>>(
         (const float2*)h->velocity.read, (const float4*)h->dye.read, (float4*)h->dye.write, a);
@@ -479,34 +560,98 @@ int fluid_pass_advect_dye(fluid_t* h, float dt) {
     return FLUID_OK;
 }
 
-// step(dt), S:1231-1294
+int fluid_pass_curl(fluid_t* h) {
+    if (!h) return FLUID_ERR_INVALID;
+    if (h->slab()) return not_on_slab(h, "fluid_pass_curl");
+    return do_curl(h, sim_grid(h));
+}
+int fluid_pass_vorticity(fluid_t* h, float dt) {
+    if (!h) return FLUID_ERR_INVALID;
+    if (h->slab()) return not_on_slab(h, "fluid_pass_vorticity");
+    return do_vorticity(h, sim_grid(h), dt);
+}
+int fluid_pass_divergence(fluid_t* h) {
+    if (!h) return FLUID_ERR_INVALID;
+    if (h->slab()) return not_on_slab(h, "fluid_pass_divergence");
+    return do_divergence(h, sim_grid(h));
+}
+int fluid_pass_curl_vorticity_divergence(fluid_t* h, float dt) {
+    if (!h) return FLUID_ERR_INVALID;
+    if (h->slab()) return not_on_slab(h, "fluid_pass_curl_vorticity_divergence");
+    return do_cvd(h, sim_grid(h), dt);
+}
+int fluid_pass_clear_pressure(fluid_t* h) {
+    if (!h) return FLUID_ERR_INVALID;
+    return run_jacobi(h, 0, true, nullptr);
+}
+int fluid_pass_jacobi(fluid_t* h, int iters) {
+    if (!h) return FLUID_ERR_INVALID;
+    if (iters < 0) return fail(h, FLUID_ERR_INVALID, "iters < 0");
+    return run_jacobi(h, iters, false, nullptr);
+}
+int fluid_pass_pressure_solve(fluid_t* h) {
+    if (!h) return FLUID_ERR_INVALID;
+    return run_jacobi(h, h->cfg.pressure_iterations, true, nullptr);
+}
+int fluid_pass_gradient_subtract(fluid_t* h) {
+    if (!h) return FLUID_ERR_INVALID;
+    if (h->slab()) return not_on_slab(h, "fluid_pass_gradient_subtract");
+    return do_gradient(h, sim_grid(h));
+}
+int fluid_pass_advect_velocity(fluid_t* h, float dt) {
+    if (!h) return FLUID_ERR_INVALID;
+    if (h->slab()) return not_on_slab(h, "fluid_pass_advect_velocity");
+    return do_advect_velocity(h, sim_grid(h), dt);
+}
+int fluid_pass_advect_dye(fluid_t* h, float dt) {
+    if (!h) return FLUID_ERR_INVALID;
+    if (h->slab()) return not_on_slab(h, "fluid_pass_advect_dye");
+    return do_advect_dye(h, dt);
+}
+
+// step(dt), S:1231-1294.
+// On a slab the only messages are the Jacobi halos (inside run_jacobi) and the two advection
+// halos below; curl / vorticity / divergence / gradientSubtract read ghost rows that the previous
+// step's advection (velocity on owned rows +- 3) and the last Jacobi launch (pressure on owned
+// rows +- 1) already computed redundantly.
 int fluid_step(fluid_t* h, float dt) {
     if (!h) return FLUID_ERR_INVALID;
     const uint64_t l0 = h->launches;
     const bool timed = (h->cfg.flags & FLUID_FLAG_NO_GRAPH) != 0;
+    const int W = h->cfg.sim_w;
     int rc;
     int jl = 0;
     if (timed) cudaEventRecord(h->tev[0], h->stream);
+    if (h->slab() && !h->v_ghost_valid) {   // after fluid_write(velocity): rebuild the +-3 ghost rows
+        if ((rc = exchange_rows(h, h->velocity.read, (size_t)W * sizeof(float2), h->roff, h->row0, h->row1, 3))) return rc;
+        h->v_ghost_valid = true;
+    }
     if (h->cfg.flags & FLUID_FLAG_UNFUSED) {
-        if ((rc = fluid_pass_curl(h))) return rc;
-        if ((rc = fluid_pass_vorticity(h, dt))) return rc;
-        if ((rc = fluid_pass_divergence(h))) return rc;
+        if ((rc = do_curl(h, sim_grid_ext(h, h->slab() ? 2 : 0)))) return rc;
+        if ((rc = do_vorticity(h, sim_grid_ext(h, h->slab() ? 1 : 0), dt))) return rc;
+        if ((rc = do_divergence(h, sim_grid(h)))) return rc;
     } else {
-        if ((rc = fluid_pass_curl_vorticity_divergence(h, dt))) return rc;
+        if ((rc = do_cvd(h, sim_grid(h), dt))) return rc;
     }
     if (timed) cudaEventRecord(h->tev[1], h->stream);
     if ((rc = run_jacobi(h, h->cfg.pressure_iterations, true, &jl))) return rc;
     if (timed) cudaEventRecord(h->tev[2], h->stream);
-    if ((rc = fluid_pass_gradient_subtract(h))) return rc;
+    if ((rc = do_gradient(h, sim_grid(h)))) return rc;
     if (timed) cudaEventRecord(h->tev[3], h->stream);
-    if ((rc = fluid_pass_advect_velocity(h, dt))) return rc;
+    if (h->slab()) {   // advection halo #1: G rows of the projected velocity
+        if ((rc = exchange_rows(h, h->velocity.read, (size_t)W * sizeof(float2), h->roff, h->row0, h->row1, h->G))) return rc;
+    }
+    if ((rc = do_advect_velocity(h, sim_grid_ext(h, h->slab() ? 3 : 0), dt))) return rc;
     if (timed) cudaEventRecord(h->tev[4], h->stream);
-    if ((rc = fluid_pass_advect_dye(h, dt))) return rc;
+    if (h->slab()) {   // advection halo #2: Gd rows of dye
+        if ((rc = exchange_rows(h, h->dye.read, (size_t)h->cfg.dye_w * sizeof(float4), h->droff, h->drow0, h->drow1, h->Gd))) return rc;
+    }
+    if ((rc = do_advect_dye(h, dt))) return rc;
     if (timed) cudaEventRecord(h->tev[5], h->stream);
     h->timing.jacobi_launches = jl;
     h->timing.total_launches = (int)(h->launches - l0);
     h->have_timing = timed;
-    return check_halo(h);
+    return FLUID_OK;
 }
 
 // splat(x,y,dx,dy,color), S:1441-1455
@@ -517,7 +662,8 @@ int fluid_splat(fluid_t* h, float x, float y, float dx, float dy, float r, float
     if (h->cfg.aspect > 1.0f) rad *= (double)h->cfg.aspect;
     const float radius = (float)rad;
     dim3 bl(64, 4);
-    Grid gs = sim_grid(h), gd = dye_grid(h);
+    // a splat is point-wise, so the +-3 velocity ghost rows are simply splatted as well
+    Grid gs = sim_grid_ext(h, h->slab() ? 3 : 0), gd = dye_grid(h);
     splat_velocity_kernel<<<grid2d(gs.W, gs.j_hi - gs.j_lo, bl), bl, 0, h->stream>>>(
         (const float2*)h->velocity.read, (float2*)h->velocity.write, gs, h->cfg.aspect, x, y, dx, dy,
         radius);
@@ -534,6 +680,7 @@ int fluid_splat(fluid_t* h, float x, float y, float dx, float dy, float r, float
 int fluid_resize(fluid_t* h, int sim_w, int sim_h, int dye_w, int dye_h) {
     if (!h) return FLUID_ERR_INVALID;
     if (sim_w < 1 || sim_h < 1 || dye_w < 1 || dye_h < 1) return fail(h, FLUID_ERR_INVALID, "bad size");
+    if (h->slab()) return not_on_slab(h, "fluid_resize");
     const int ow = h->cfg.sim_w, oh = h->cfg.sim_h, odw = h->cfg.dye_w, odh = h->cfg.dye_h;
     dim3 b(64, 4);
     const size_t n = (size_t)sim_w * sim_h, nd = (size_t)dye_w * dye_h;
@@ -573,7 +720,7 @@ int fluid_resize(fluid_t* h, int sim_w, int sim_h, int dye_w, int dye_h) {
     CU(cudaMemsetAsync(h->divergence, 0, n * sizeof(float), h->stream));
     CU(cudaMemsetAsync(h->curl, 0, n * sizeof(float), h->stream));
     h->cfg.sim_w = sim_w; h->cfg.sim_h = sim_h; h->cfg.dye_w = dye_w; h->cfg.dye_h = dye_h;
-    h->row0 = 0; h->row1 = sim_h; h->drow0 = 0; h->drow1 = dye_h;
+    h->row0 = 0; h->row1 = sim_h; h->drow0 = 0; h->drow1 = dye_h; h->roff = 0; h->droff = 0;
     return FLUID_OK;
 }
 
@@ -600,7 +747,7 @@ int fluid_read(fluid_t* h, int field, float* host, size_t n_floats) {
     if (n_floats != n) return fail(h, FLUID_ERR_INVALID, "field %d has %zu floats, caller passed %zu", field, n, n_floats);
     CU(cudaMemcpyAsync(host, p, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    return FLUID_OK;
+    return check_halo(h);
 }
 
 int fluid_write(fluid_t* h, int field, const float* host, size_t n_floats) {
@@ -610,18 +757,20 @@ int fluid_write(fluid_t* h, int field, const float* host, size_t n_floats) {
     if (n_floats != n) return fail(h, FLUID_ERR_INVALID, "field %d has %zu floats, caller passed %zu", field, n, n_floats);
     CU(cudaMemcpyAsync(p, host, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    if (field == FLUID_FIELD_VELOCITY) h->v_ghost_valid = false;   // ghosts rebuilt by the next step
     return FLUID_OK;
 }
 
 int fluid_pressure_solve_host(fluid_t* h, const float* div_host, float* p_host, int iters) {
     if (!h || !div_host || !p_host || iters < 0) return fail(h, FLUID_ERR_INVALID, "bad argument");
-    const size_t n = sim_cells(h);
+    const size_t n = (size_t)h->cfg.sim_w * (h->row1 - h->row0);   // owned rows
+    const size_t go = (size_t)h->G * h->cfg.sim_w;
     // Host buffers may be pageable; pinned ones (cudaHostAlloc / cudaHostRegister by the caller)
     // make the copies asynchronous DMA.  Either way all three copies are inside this call.
-    CU(cudaMemcpyAsync(h->divergence, div_host, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemcpyAsync(h->pressure.read, p_host, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->divergence + go, div_host, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync((float*)h->pressure.read + go, p_host, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     int rc = run_jacobi(h, iters, true, nullptr); if (rc) return rc;
-    CU(cudaMemcpyAsync(p_host, h->pressure.read, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(p_host, (float*)h->pressure.read + go, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return FLUID_OK;
 }

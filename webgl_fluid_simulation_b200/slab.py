@@ -1,0 +1,71 @@
+"""Row-slab decomposition plan — the host-side arithmetic of the multi-GPU path.
+
+Mirrors csrc/fluid.cu (create_common / run_jacobi / fluid_step) so that the schedule can be
+checked on CPU (tests/test_slab_schedule_gloo.py) and so that launchers know which rows a rank owns.
+One process per GPU; rank g of G owns sim rows [g*H//G, (g+1)*H//G) and the matching dye rows.
+Messages (NCCL send/recv inside the library, both neighbours in one group) happen ONLY on:
+  * Jacobi: once per solve  kmax rows of divergence; before each launch of depth K: K rows of
+    pressure (K+1 before the last launch, which also produces one row beyond each slab edge so that
+    gradientSubtract needs no message);
+  * advection: G rows of the projected velocity, then Gd rows of dye.
+curl / vorticity / divergence run on ghost rows the previous step computed redundantly
+(velocity is advected on owned rows +-3: curl needs +-2, vorticity +-1, divergence +-0).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+KMAX = 12
+DEFAULT_BLOCK = 10
+DEFAULT_HALO = 32
+VELOCITY_GHOST = 3
+
+
+def rows(extent: int, rank: int, world: int) -> tuple[int, int]:
+    return extent * rank // world, extent * (rank + 1) // world
+
+
+def jacobi_launches(iters: int, block: int = DEFAULT_BLOCK) -> list[int]:
+    """Balanced split of `iters` sweeps into ceil(iters/block) launches (run_jacobi)."""
+    if iters <= 0:
+        return []
+    block = max(1, min(block, KMAX))
+    n = (iters + block - 1) // block
+    base, extra = divmod(iters, n)
+    return [base + (1 if k < extra else 0) for k in range(n)]
+
+
+@dataclass
+class SlabPlan:
+    sim_h: int
+    dye_h: int
+    rank: int
+    world: int
+    halo: int = DEFAULT_HALO
+
+    def __post_init__(self):
+        self.row0, self.row1 = rows(self.sim_h, self.rank, self.world)
+        self.drow0, self.drow1 = rows(self.dye_h, self.rank, self.world)
+        self.G = self.halo if self.world > 1 else 0
+        self.Gd = self.G * max(1, -(-self.dye_h // self.sim_h))
+        if self.world > 1 and (self.row1 - self.row0 < self.G or self.drow1 - self.drow0 < self.Gd):
+            raise ValueError(f"slab of {self.row1 - self.row0} rows is shorter than the {self.G}-row halo")
+
+    def block(self, requested: int = 0) -> int:
+        kb = requested if requested > 0 else DEFAULT_BLOCK
+        kb = min(kb, KMAX)
+        return min(kb, self.G - 1) if self.world > 1 else kb
+
+    def jacobi_messages(self, iters: int, requested_block: int = 0):
+        """[(field, rows)] in issue order for one pressure solve."""
+        ks = jacobi_launches(iters, self.block(requested_block))
+        if not ks or self.world == 1:
+            return []
+        msgs = [("divergence", max(ks))]
+        for i, k in enumerate(ks):
+            msgs.append(("pressure", k + (1 if i == len(ks) - 1 else 0)))
+        return msgs
+
+    def max_backtrace_rows(self) -> int:
+        """Largest dt*|v| (in sim rows) the advection halo covers: G - ghost compute - bilinear tap."""
+        return self.G - VELOCITY_GHOST - 2
