@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 W, H, WD, HD = 64, 96, 96, 192
-ITERS, DT, HALO = 23, 0.016666, 14
+ITERS, DT, HALO = 23, 0.016666, 14   # halo >= iterations+2 is added by the plan when it fits
 NSTEPS = 3
 
 
@@ -46,12 +46,12 @@ def _poison(arr, lo, hi):
     return out
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, q_iters):
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from oracle import oracle as O
     from webgl_fluid_simulation_b200.slab import SlabPlan, jacobi_launches
-    plan = SlabPlan(H, HD, rank, world, halo=HALO)
+    plan = SlabPlan(H, HD, rank, world, halo=HALO, iterations=q_iters)
     r0, r1, d0, d1, G, Gd = plan.row0, plan.row1, plan.drow0, plan.drow1, plan.G, plan.Gd
     rng = np.random.default_rng(0)                      # same on every rank
     v = (rng.standard_normal((H, W, 2)) * 40).astype(np.float32)
@@ -67,16 +67,21 @@ def _worker(rank, world, port, q):
             c = O.curl(v)                                            # valid owned +-2
             v = O.vorticity(v, c, 30.0, DT)                          # valid owned +-1
             div = _poison(O.divergence(v), r0, r1)                   # valid owned
-            ks = jacobi_launches(ITERS, plan.block())
-            _exchange(div, r0, r1, max(ks), rank, world)
-            for i, k in enumerate(ks):
-                n = k + (1 if i == len(ks) - 1 else 0)
-                _exchange(p, r0, r1, n, rank, world)
-                p = _poison(p, r0 - n, r1 + n)
+            ext_of = plan.launch_extents(ITERS)
+            deep = plan.deep(ITERS)
+            if deep:                                                 # one group: p (iters+1) + div (iters)
+                _exchange(p, r0, r1, ITERS + 1, rank, world); p = _poison(p, r0 - ITERS - 1, r1 + ITERS + 1)
+                _exchange(div, r0, r1, ITERS, rank, world)
+            else:
+                _exchange(div, r0, r1, max(k for k, _ in ext_of), rank, world)
+            for i, (k, ext) in enumerate(ext_of):
+                if not deep:
+                    _exchange(p, r0, r1, k + ext, rank, world)
+                    p = _poison(p, r0 - k - ext, r1 + k + ext)
                 if i == 0:
                     p = O.clear(p, 0.8)
                 p = O.jacobi(p, div, k)
-                p = _poison(p, r0 - (n - k), r1 + (n - k))           # what the launch writes
+                p = _poison(p, r0 - ext, r1 + ext)                   # what the launch writes
             v = _poison(O.gradient_subtract(p, v), r0, r1)           # valid owned
             _exchange(v, r0, r1, G, rank, world)
             v = _poison(O.advect(v, v, DT, 0.2), r0 - 3, r1 + 3)     # redundant ghost compute
@@ -95,12 +100,14 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_slab_schedule_is_exact(world):
+@pytest.mark.parametrize("world,plan_iters", [(2, ITERS), (3, ITERS), (2, 5)])
+def test_slab_schedule_is_exact(world, plan_iters):
+    """plan_iters = ITERS: ghost zone sized for the deep (one message per solve) form;
+    plan_iters = 5: ghost zone too thin for 23 sweeps -> per-launch fallback."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29650 + world
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    port = 29650 + world + plan_iters
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, plan_iters)) for r in range(world)]
     for pr in procs:
         pr.start()
     res = sorted(q.get(timeout=180) for _ in procs)
@@ -114,9 +121,13 @@ def test_plan_arithmetic():
     assert jacobi_launches(50, 10) == [10] * 5 and jacobi_launches(50, 8) == [8, 7, 7, 7, 7, 7, 7]
     assert jacobi_launches(20, 12) == [10, 10] and jacobi_launches(0) == [] and sum(jacobi_launches(37, 9)) == 37
     assert [rows(10, r, 3) for r in range(3)] == [(0, 3), (3, 6), (6, 10)]
-    pl = SlabPlan(8192, 8192, 3, 8)
-    assert (pl.row0, pl.row1, pl.G, pl.Gd) == (3072, 4096, 32, 32)
-    assert pl.jacobi_messages(40) == [("divergence", 10)] + [("pressure", 10)] * 3 + [("pressure", 11)]
+    pl = SlabPlan(8192, 8192, 3, 8, iterations=40)
+    assert (pl.row0, pl.row1, pl.G, pl.Gd) == (3072, 4096, 42, 42)
+    assert pl.jacobi_messages(40) == [("pressure+divergence", 41)]
+    assert pl.launch_extents(40) == [(10, 31), (10, 21), (10, 11), (10, 1)]
+    thin = SlabPlan(8192, 8192, 3, 8, iterations=5)                 # iterations raised after creation
+    assert thin.G == 32 and not thin.deep(40)
+    assert thin.jacobi_messages(40) == [("divergence", 10)] + [("pressure", 10)] * 3 + [("pressure", 11)]
     assert SlabPlan(4096, 4096, 0, 1).jacobi_messages(50) == []
     with pytest.raises(ValueError):
-        SlabPlan(128, 128, 0, 8)
+        SlabPlan(64, 64, 0, 8)          # 8-row slabs cannot hold a 14-row halo

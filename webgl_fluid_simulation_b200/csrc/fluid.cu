@@ -59,6 +59,7 @@ struct fluid {
     int roff = 0, droff = 0;         // global row index of local row 0  (row0 - G, drow0 - Gd)
     ncdl::ncclComm_t comm = nullptr;
     bool v_ghost_valid = true;       // velocity valid on owned rows +-3 (what the next step needs)
+    uint64_t halo_groups = 0;        // NCCL groups issued (diagnostics)
     bool slab() const { return world > 1; }
     int lrows() const { return row1 - row0 + 2 * G; }
     int ldrows() const { return drow1 - drow0 + 2 * Gd; }
@@ -111,29 +112,45 @@ int check_launch(fluid_t* h, const char* what, int n = 1) {
     return FLUID_OK;
 }
 
-// ---- halo exchange (NCCL point-to-point, both neighbours in one group) -----------------------------
-// Sends my top `n` owned rows up and my bottom `n` owned rows down; receives the neighbours' rows
-// into my ghost rows.  `base` is local row 0 of a buffer whose local row 0 is global row `off`.
-int exchange_rows(fluid_t* h, void* base, size_t row_bytes, int off, int r0, int r1, int n) {
-    if (!h->slab() || n <= 0) return FLUID_OK;
-    if (n > r1 - r0)
-        return fail(h, FLUID_ERR_HALO, "halo of %d rows exceeds the slab height %d (use fewer GPUs or a taller grid)", n, r1 - r0);
+// ---- halo exchange (NCCL point-to-point; all buffers and both neighbours in ONE group) ------------
+// For each item: sends my top `n` owned rows up and my bottom `n` owned rows down, receives the
+// neighbours' rows into my ghost rows.  `base` is local row 0 of a buffer whose local row 0 is
+// global row `off`.  Halo messages are latency-bound (a 4096-float row is 16 KiB), so everything
+// that can travel together does.
+struct HaloItem { void* base; size_t row_bytes; int off, r0, r1, n; };
+
+int exchange_many(fluid_t* h, const HaloItem* it, int count) {
+    if (!h->slab()) return FLUID_OK;
     ncdl::Api& N = ncdl::api();
-    char* b = static_cast<char*>(base);
-    auto at = [&](int grow) { return b + (size_t)(grow - off) * row_bytes; };
-    const size_t bytes = (size_t)n * row_bytes;
+    for (int k = 0; k < count; ++k)
+        if (it[k].n > it[k].r1 - it[k].r0)
+            return fail(h, FLUID_ERR_HALO, "halo of %d rows exceeds the slab height %d (use fewer GPUs or a taller grid)",
+                        it[k].n, it[k].r1 - it[k].r0);
     int rc = N.GroupStart();
-    if (h->rank + 1 < h->world) {
-        if (!rc) rc = N.Send(at(r1 - n), bytes, ncdl::ncclInt8, h->rank + 1, h->comm, h->stream);
-        if (!rc) rc = N.Recv(at(r1), bytes, ncdl::ncclInt8, h->rank + 1, h->comm, h->stream);
-    }
-    if (h->rank > 0) {
-        if (!rc) rc = N.Send(at(r0), bytes, ncdl::ncclInt8, h->rank - 1, h->comm, h->stream);
-        if (!rc) rc = N.Recv(at(r0 - n), bytes, ncdl::ncclInt8, h->rank - 1, h->comm, h->stream);
+    for (int k = 0; k < count && !rc; ++k) {
+        const HaloItem& q = it[k];
+        if (q.n <= 0) continue;
+        char* b = static_cast<char*>(q.base);
+        auto at = [&](int grow) { return b + (size_t)(grow - q.off) * q.row_bytes; };
+        const size_t bytes = (size_t)q.n * q.row_bytes;
+        if (h->rank + 1 < h->world) {
+            if (!rc) rc = N.Send(at(q.r1 - q.n), bytes, ncdl::ncclInt8, h->rank + 1, h->comm, h->stream);
+            if (!rc) rc = N.Recv(at(q.r1), bytes, ncdl::ncclInt8, h->rank + 1, h->comm, h->stream);
+        }
+        if (h->rank > 0) {
+            if (!rc) rc = N.Send(at(q.r0), bytes, ncdl::ncclInt8, h->rank - 1, h->comm, h->stream);
+            if (!rc) rc = N.Recv(at(q.r0 - q.n), bytes, ncdl::ncclInt8, h->rank - 1, h->comm, h->stream);
+        }
     }
     const int rc2 = N.GroupEnd();
     if (rc || rc2) return fail(h, FLUID_ERR_NCCL, "NCCL halo exchange failed: %s", N.GetErrorString(rc ? rc : rc2));
+    ++h->halo_groups;
     return FLUID_OK;
+}
+
+int exchange_rows(fluid_t* h, void* base, size_t row_bytes, int off, int r0, int r1, int n) {
+    HaloItem it{base, row_bytes, off, r0, r1, n};
+    return exchange_many(h, &it, 1);
 }
 
 // ---- Jacobi dispatch -----------------------------------------------------------------------------
@@ -201,7 +218,7 @@ int run_jacobi(fluid_t* h, int iters, bool scale_first, int* launches_out) {
     a.scale = h->cfg.pressure;
     int kb = h->cfg.jacobi_block > 0 ? h->cfg.jacobi_block : 10;  // tuned on B200: profiles/r01_tune_jacobi.txt
     kb = std::min(kb, KMAX);
-    if (h->slab()) kb = std::min(kb, h->G - 1);
+    if (h->slab()) kb = std::max(1, std::min(kb, h->G - 1));
     const bool naive = (h->cfg.flags & FLUID_FLAG_NAIVE_JACOBI) || kb == 1;
     if (iters <= 0) {
         if (scale_first) {   // clear pass alone (owned + ghost rows; ghosts are refreshed before use anyway)
@@ -217,20 +234,39 @@ int run_jacobi(fluid_t* h, int iters, bool scale_first, int* launches_out) {
     const bool blocked = tb_eligible(h) && !naive;
     const int nlaunch = blocked ? (iters + kb - 1) / kb : iters;
     const int base = iters / nlaunch, extra = iters % nlaunch;
-    if (h->slab()) {   // divergence ghost rows: the deepest launch needs kmax rows (incl. the +1 extension)
-        const int kmax = base + (extra ? 1 : 0);
-        int rc = exchange_rows(h, h->divergence, (size_t)W * sizeof(float), h->roff, h->row0, h->row1, kmax);
-        if (rc) return rc;
+    // Slab halos.  Communication-avoiding form (deep): ONE group per solve carries iters+1 rows of
+    // pressure and iters rows of divergence; launch i then produces owned rows +- (sweeps still to
+    // come + 1), so later launches find their input already there (~1 % redundant rows instead of
+    // one latency-bound message per launch).  If the ghost zone is too thin for that (iterations
+    // raised after creation) fall back to one K-row message per launch.
+    const bool deep = h->slab() && (iters + 1 <= h->G) && (iters + 1 <= h->row1 - h->row0);
+    if (h->slab()) {
+        if (deep) {
+            HaloItem it[2] = {{h->pressure.read, (size_t)W * sizeof(float), h->roff, h->row0, h->row1, iters + 1},
+                              {h->divergence, (size_t)W * sizeof(float), h->roff, h->row0, h->row1, iters}};
+            int rc = exchange_many(h, it, 2); if (rc) return rc;
+        } else {
+            const int kmax = base + (extra ? 1 : 0);
+            int rc = exchange_rows(h, h->divergence, (size_t)W * sizeof(float), h->roff, h->row0, h->row1, kmax);
+            if (rc) return rc;
+        }
     }
+    int remaining = iters;
     for (int k = 0; k < nlaunch; ++k) {
         const int K = base + (k < extra ? 1 : 0);
         const bool last = (k == nlaunch - 1);
+        remaining -= K;
         a.pin = (const float*)h->pressure.read; a.pout = (float*)h->pressure.write;
         a.out_lo = h->row0; a.out_hi = h->row1;
         if (h->slab()) {
-            const int ext = last ? 1 : 0;
-            int rc = exchange_rows(h, h->pressure.read, (size_t)W * sizeof(float), h->roff, h->row0, h->row1, K + ext);
-            if (rc) return rc;
+            int ext;
+            if (deep) {
+                ext = remaining + 1;
+            } else {
+                ext = last ? 1 : 0;
+                int rc = exchange_rows(h, h->pressure.read, (size_t)W * sizeof(float), h->roff, h->row0, h->row1, K + ext);
+                if (rc) return rc;
+            }
             a.out_lo = std::max(h->row0 - ext, 0); a.out_hi = std::min(h->row1 + ext, H);
         }
         const bool sc = scale_first && k == 0;
@@ -349,12 +385,18 @@ int create_common(const fluid_config* cfg, int rank, int world, const void* uid,
     h->row0 = (int)((long long)H * rank / world);  h->row1 = (int)((long long)H * (rank + 1) / world);
     h->drow0 = (int)((long long)Hd * rank / world); h->drow1 = (int)((long long)Hd * (rank + 1) / world);
     if (world > 1) {
-        int g = 32;                                   // rows: 3 (ghost compute) + dt*|v|max + 2, see DESIGN.md
+        // ghost rows: enough for the advection back-trace (3 ghost-compute rows + dt*|v|max + 2)
+        // and for the deep Jacobi halo (iterations + 1), see DESIGN.md §7
+        int g = std::max(32, cfg->pressure_iterations + 2);
         if (const char* e = getenv("FLUID_HALO_ROWS")) g = std::max(14, atoi(e));
+        // every rank must arrive at the SAME halo height (message sizes must match), so clip with
+        // the height of the shortest slab, which all ranks can compute: floor(H / world)
+        const int per = std::max(1, (Hd + H - 1) / H);
+        g = std::min(g, std::min(H / world, (Hd / world) / per));
         h->G = g;
-        h->Gd = g * std::max(1, (Hd + H - 1) / H);   // same physical reach on the dye grid
-        if (h->row1 - h->row0 < h->G || h->drow1 - h->drow0 < h->Gd) {
-            int rc = fail(nullptr, FLUID_ERR_INVALID, "slab of %d rows is shorter than the %d-row halo", h->row1 - h->row0, h->G);
+        h->Gd = g * per;                              // same physical reach on the dye grid
+        if (g < 14) {
+            int rc = fail(nullptr, FLUID_ERR_INVALID, "slabs of %d rows are too short for a 14-row halo: use fewer GPUs", H / world);
             delete h; return rc;
         }
     }

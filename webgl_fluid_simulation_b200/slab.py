@@ -4,9 +4,11 @@ Mirrors csrc/fluid.cu (create_common / run_jacobi / fluid_step) so that the sche
 checked on CPU (tests/test_slab_schedule_gloo.py) and so that launchers know which rows a rank owns.
 One process per GPU; rank g of G owns sim rows [g*H//G, (g+1)*H//G) and the matching dye rows.
 Messages (NCCL send/recv inside the library, both neighbours in one group) happen ONLY on:
-  * Jacobi: once per solve  kmax rows of divergence; before each launch of depth K: K rows of
-    pressure (K+1 before the last launch, which also produces one row beyond each slab edge so that
-    gradientSubtract needs no message);
+  * Jacobi, communication-avoiding ("deep") form: ONE group per solve with iters+1 rows of pressure
+    and iters rows of divergence; launch i then produces owned rows +- (sweeps still to come + 1).
+    Fallback when the ghost zone is thinner than iters+1: kmax rows of divergence once, then K rows
+    of pressure before each launch of depth K (K+1 before the last, which also produces one row
+    beyond each slab edge so that gradientSubtract needs no message);
   * advection: G rows of the projected velocity, then Gd rows of dye.
 curl / vorticity / divergence run on ghost rows the previous step computed redundantly
 (velocity is advected on owned rows +-3: curl needs +-2, vorticity +-1, divergence +-0).
@@ -42,14 +44,19 @@ class SlabPlan:
     rank: int
     world: int
     halo: int = DEFAULT_HALO
+    iterations: int = 20
 
     def __post_init__(self):
         self.row0, self.row1 = rows(self.sim_h, self.rank, self.world)
         self.drow0, self.drow1 = rows(self.dye_h, self.rank, self.world)
-        self.G = self.halo if self.world > 1 else 0
+        self.G = 0
+        if self.world > 1:
+            per_sim = max(1, -(-self.dye_h // self.sim_h))
+            # clipped with the SHORTEST slab (floor(H/world)) so that all ranks agree on the halo height
+            self.G = min(max(self.halo, self.iterations + 2), self.sim_h // self.world, (self.dye_h // self.world) // per_sim)
         self.Gd = self.G * max(1, -(-self.dye_h // self.sim_h))
-        if self.world > 1 and (self.row1 - self.row0 < self.G or self.drow1 - self.drow0 < self.Gd):
-            raise ValueError(f"slab of {self.row1 - self.row0} rows is shorter than the {self.G}-row halo")
+        if self.world > 1 and self.G < 14:
+            raise ValueError(f"slab of {self.row1 - self.row0} rows is too short for a 14-row halo")
 
     def block(self, requested: int = 0) -> int:
         kb = requested if requested > 0 else DEFAULT_BLOCK
@@ -61,10 +68,29 @@ class SlabPlan:
         ks = jacobi_launches(iters, self.block(requested_block))
         if not ks or self.world == 1:
             return []
+        if self.deep(iters):
+            return [("pressure+divergence", iters + 1)]
         msgs = [("divergence", max(ks))]
         for i, k in enumerate(ks):
             msgs.append(("pressure", k + (1 if i == len(ks) - 1 else 0)))
         return msgs
+
+    def deep(self, iters: int) -> bool:
+        return self.world > 1 and iters + 1 <= self.G and iters + 1 <= self.row1 - self.row0
+
+    def launch_extents(self, iters: int, requested_block: int = 0):
+        """[(K, ext)]: launch of depth K produces owned rows +- ext (clipped to the domain)."""
+        ks = jacobi_launches(iters, self.block(requested_block))
+        out, rem = [], iters
+        for i, k in enumerate(ks):
+            rem -= k
+            if self.world == 1:
+                out.append((k, 0))
+            elif self.deep(iters):
+                out.append((k, rem + 1))
+            else:
+                out.append((k, 1 if i == len(ks) - 1 else 0))
+        return out
 
     def max_backtrace_rows(self) -> int:
         """Largest dt*|v| (in sim rows) the advection halo covers: G - ghost compute - bilinear tap."""
