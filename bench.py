@@ -211,9 +211,16 @@ def main():
         ms = time_steps(sim, solve, args.steps)
         sim.sync()
         # keep the device loaded until NVML has a few samples even if the timed region is short
-        t_end = time.time() + 0.25
-        while len(clk.samples) < 5 and time.time() < t_end:
-            solve(); sim.sync()
+        # (single GPU only: on slabs every solve is a collective, so all ranks must issue the
+        # same number of them; there a fixed number of extra solves keeps the sampler fed)
+        if world == 1:
+            t_end = time.time() + 0.25
+            while len(clk.samples) < 5 and time.time() < t_end:
+                solve(); sim.sync()
+        else:
+            for _ in range(20):
+                solve()
+            sim.sync()
     barrier()
     # exact launch count of the timed region: launches per solve x steps
     l1 = sim.launch_count(); solve(); sim.sync(); per_step_launches = sim.launch_count() - l1
