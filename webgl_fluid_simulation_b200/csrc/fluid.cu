@@ -87,6 +87,8 @@ int fail(fluid_t* h, int code, const char* fmt, ...) {
                         __FILE__, __LINE__);                                                  \
     } while (0)
 
+inline bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
+
 inline dim3 grid2d(int W, int rows, dim3 b) {
     return dim3((W + b.x - 1) / b.x, (rows + b.y - 1) / b.y);
 }
@@ -581,7 +583,10 @@ static int do_advect_velocity(fluid_t* h, Grid out, float dt) {
     valid_rows(h->row0, h->row1, h->G, h->cfg.sim_h, &a.vel_lo, &a.vel_hi);
     a.src_lo = a.vel_lo; a.src_hi = a.vel_hi;
     a.dt = dt; a.dissipation = h->cfg.velocity_dissipation; a.halo_violation = h->halo_flag;
-    advect_velocity_kernel<<<grid2d(out.W, out.j_hi - out.j_lo, b), b, 0, h->stream>>>(
+    const bool p2 = is_pow2(h->cfg.sim_w) && is_pow2(h->cfg.sim_h);
+    if (p2) advect_velocity_kernel<true><<<grid2d(out.W, out.j_hi - out.j_lo, b), b, 0, h->stream>>>(
+        (const float2*)h->velocity.read, (float2*)h->velocity.write, a);
+    else advect_velocity_kernel<false><<<grid2d(out.W, out.j_hi - out.j_lo, b), b, 0, h->stream>>>(
         (const float2*)h->velocity.read, (float2*)h->velocity.write, a);
     int rc = check_launch(h, "advect_velocity_kernel"); if (rc) return rc;
     h->velocity.swap();                                   // S:1285
@@ -595,8 +600,13 @@ static int do_advect_dye(fluid_t* h, float dt) {
     valid_rows(h->row0, h->row1, h->slab() ? 3 : 0, h->cfg.sim_h, &a.vel_lo, &a.vel_hi);
     valid_rows(h->drow0, h->drow1, h->Gd, h->cfg.dye_h, &a.src_lo, &a.src_hi);
     a.dt = dt; a.dissipation = h->cfg.density_dissipation; a.halo_violation = h->halo_flag;
-    advect_dye_kernel<<<grid2d(a.src.W, a.src.j_hi - a.src.j_lo, b), b, 0, h->stream>>>(
-        (const float2*)h->velocity.read, (const float4*)h->dye.read, (float4*)h->dye.write, a);
+    const bool p2 = is_pow2(h->cfg.sim_w) && is_pow2(h->cfg.sim_h) && is_pow2(h->cfg.dye_w) && is_pow2(h->cfg.dye_h);
+    const bool same = h->cfg.sim_w == h->cfg.dye_w && h->cfg.sim_h == h->cfg.dye_h;
+    const dim3 gr = grid2d(a.src.W, a.src.j_hi - a.src.j_lo, b);
+    const float2* V = (const float2*)h->velocity.read; const float4* Dr = (const float4*)h->dye.read; float4* Dw = (float4*)h->dye.write;
+    if (p2 && same) advect_dye_kernel<true, true><<<gr, b, 0, h->stream>>>(V, Dr, Dw, a);
+    else if (p2) advect_dye_kernel<true, false><<<gr, b, 0, h->stream>>>(V, Dr, Dw, a);
+    else advect_dye_kernel<false, false><<<gr, b, 0, h->stream>>>(V, Dr, Dw, a);
     int rc = check_launch(h, "advect_dye_kernel"); if (rc) return rc;
     h->dye.swap();                                        // S:1293
     return FLUID_OK;
