@@ -117,7 +117,13 @@ def cpu_port_rate(budget_s=12.0, cap=100000):
     t0 = time.perf_counter(); O.jacobi(p, d, 2); t1 = time.perf_counter()
     per = (t1 - t0) / 2
     n = int(max(2, min(cap, budget_s / max(per, 1e-6))))
-    t0 = time.perf_counter(); O.jacobi(p, d, n); dt = time.perf_counter() - t0
+    t0 = time.perf_counter(); done = 0
+    while True:                                          # the calibration above can be cold: run to the budget
+        O.jacobi(p, d, n); done += n
+        dt = time.perf_counter() - t0
+        if dt >= 0.8 * budget_s:
+            break
+    n = done
     return (W * H * n / dt, O.num_threads(),
             f"{n} Jacobi sweeps of {W}x{H} fp32 (= {n / ITERS:.1f} x the {ITERS}-sweep solve), {dt:.1f} s of CPU time")
 
@@ -166,6 +172,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--jacobi-block", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--quick", action="store_true", help="timed region only (tuning runs): no e2e / naive / full-step / cpu legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -261,6 +268,13 @@ def main():
         "clocks": clk.summary(), "gpu_launches": gpu_launches, "roofline": roofline,
     }
 
+    if args.quick:
+        if rank == 0:
+            print(json.dumps(out))
+        sim.close()
+        if dist:
+            dist.barrier(); dist.destroy_process_group()
+        return
     # ---- e2e: host buffers through the C ABI; every rank moves its own slab -----------------------
     ph = torch.empty((H, W), dtype=torch.float32).pin_memory()
     dh = torch.empty((H, W), dtype=torch.float32).pin_memory()
