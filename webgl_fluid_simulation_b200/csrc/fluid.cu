@@ -59,7 +59,20 @@ struct fluid {
     int roff = 0, droff = 0;         // global row index of local row 0  (row0 - G, drow0 - Gd)
     ncdl::ncclComm_t comm = nullptr;
     bool v_ghost_valid = true;       // velocity valid on owned rows +-3 (what the next step needs)
-    uint64_t halo_groups = 0;        // NCCL groups issued (diagnostics)
+    uint64_t halo_groups = 0;        // halo exchanges issued (diagnostics)
+    // ---- peer-memory halo path (fluid_p2p_export / fluid_p2p_connect) -------------------------------
+    char* arena = nullptr;           // slab mode: every exchanged field + the flag words live in ONE allocation
+    size_t arena_bytes = 0;
+    size_t off_v[2] = {0, 0}, off_p[2] = {0, 0}, off_dye[2] = {0, 0}, off_div = 0, off_flags = 0;
+    int par_v = 0, par_p = 0, par_dye = 0;   // which half of a pair is .read (toggles with swap(); SPMD-identical)
+    struct Peer {
+        bool present = false;
+        char* base = nullptr;        // neighbour's arena mapped here through CUDA IPC
+        int roff = 0, droff = 0;     // neighbour's local-row-0 global row indices
+        size_t off_v[2], off_p[2], off_dye[2], off_div, off_flags;
+    } peer[2];                       // [0] = rank-1 (below), [1] = rank+1 (above)
+    bool p2p = false;
+    uint32_t p2p_seq = 0;
     bool slab() const { return world > 1; }
     int lrows() const { return row1 - row0 + 2 * G; }
     int ldrows() const { return drow1 - drow0 + 2 * Gd; }
@@ -68,6 +81,10 @@ struct fluid {
 namespace {
 
 using namespace fk;
+
+inline void swap_v(fluid_t* h) { h->velocity.swap(); h->par_v ^= 1; }
+inline void swap_p(fluid_t* h) { h->pressure.swap(); h->par_p ^= 1; }
+inline void swap_dye(fluid_t* h) { h->dye.swap(); h->par_dye ^= 1; }
 
 int fail(fluid_t* h, int code, const char* fmt, ...) {
     char buf[512];
@@ -119,15 +136,111 @@ int check_launch(fluid_t* h, const char* what, int n = 1) {
 // neighbours' rows into my ghost rows.  `base` is local row 0 of a buffer whose local row 0 is
 // global row `off`.  Halo messages are latency-bound (a 4096-float row is 16 KiB), so everything
 // that can travel together does.
-struct HaloItem { void* base; size_t row_bytes; int off, r0, r1, n; };
+// `which` names the buffer for the peer-memory path: 0 velocity.read, 1 pressure.read, 2 dye.read,
+// 3 divergence (the neighbour's copy of the same buffer is found through its exported offsets and
+// the SPMD-identical swap parity).
+enum { HB_VELOCITY = 0, HB_PRESSURE = 1, HB_DYE = 2, HB_DIVERGENCE = 3 };
+struct HaloItem { void* base; size_t row_bytes; int off, r0, r1, n; int which; };
+
+struct PushSeg { const float4* src; float4* dst; unsigned long long n4; };
+struct PushArgs { PushSeg seg[8]; int count; };
+
+// Writes this rank's boundary rows straight into the neighbours' ghost rows: dst pointers are the
+// neighbours' buffers mapped through CUDA IPC, so the stores travel over NVLink / NVSwitch.
+__global__ void __launch_bounds__(256) halo_push_kernel(PushArgs a) {
+    for (int k = 0; k < a.count; ++k) {
+        const float4* __restrict__ s = a.seg[k].src;
+        float4* __restrict__ d = a.seg[k].dst;
+        const unsigned long long n4 = a.seg[k].n4;
+        for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+             i += (unsigned long long)gridDim.x * blockDim.x)
+            d[i] = s[i];
+    }
+}
+
+typedef int (*PFN_memop32)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
+struct MemOps { PFN_memop32 write = nullptr, wait = nullptr; bool ok = false; };
+MemOps& memops() {
+    static MemOps m;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        cudaDriverEntryPointQueryResult q;
+        void *w = nullptr, *t = nullptr;
+        if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &w, cudaEnableDefault, &q) == cudaSuccess && w &&
+            cudaGetDriverEntryPoint("cuStreamWaitValue32", &t, cudaEnableDefault, &q) == cudaSuccess && t) {
+            m.write = (PFN_memop32)w; m.wait = (PFN_memop32)t; m.ok = true;
+        }
+    }
+    return m;
+}
+
+// flag words (uint32) at arena + off_flags:  [0] ready-from-below  [1] ready-from-above
+//                                            [2] free-from-below   [3] free-from-above
+// "ready" = the neighbour's rows for exchange `seq` have landed in my ghost rows;
+// "free"  = the neighbour has finished every kernel that read the ghost rows I fill, up to `seq`.
+int exchange_p2p(fluid_t* h, const HaloItem* it, int count) {
+    MemOps& M = memops();
+    const uint32_t seq = ++h->p2p_seq;
+    auto my_flag = [&](int idx) { return (unsigned long long)(uintptr_t)(h->arena + h->off_flags + 4 * idx); };
+    auto peer_flag = [&](int side, int idx) { return (unsigned long long)(uintptr_t)(h->peer[side].base + h->peer[side].off_flags + 4 * idx); };
+    // (a) tell both neighbours that my ghost rows may be overwritten (stream-ordered after every
+    //     kernel of mine that read them); a neighbour BELOW me sees me as its ABOVE neighbour.
+    for (int side = 0; side < 2; ++side)
+        if (h->peer[side].present && M.write(h->stream, peer_flag(side, side == 0 ? 3 : 2), seq, 0))
+            return fail(h, FLUID_ERR_CUDA, "cuStreamWriteValue32 failed");
+    // (b) wait until their ghost rows are free
+    for (int side = 0; side < 2; ++side)
+        if (h->peer[side].present && M.wait(h->stream, my_flag(side == 0 ? 2 : 3), seq, 0 /* GEQ */))
+            return fail(h, FLUID_ERR_CUDA, "cuStreamWaitValue32 failed");
+    // (c) push
+    PushArgs pa{}; pa.count = 0;
+    unsigned long long total4 = 0;
+    for (int k = 0; k < count; ++k) {
+        const HaloItem& q = it[k];
+        if (q.n <= 0) continue;
+        for (int side = 0; side < 2; ++side) {
+            const fluid::Peer& P = h->peer[side];
+            if (!P.present) continue;
+            size_t poff; int proff;
+            switch (q.which) {
+                case HB_VELOCITY: poff = P.off_v[h->par_v]; proff = P.roff; break;
+                case HB_PRESSURE: poff = P.off_p[h->par_p]; proff = P.roff; break;
+                case HB_DYE: poff = P.off_dye[h->par_dye]; proff = P.droff; break;
+                default: poff = P.off_div; proff = P.roff; break;
+            }
+            const int g0 = (side == 1) ? q.r1 - q.n : q.r0;          // my owned rows that the neighbour needs
+            const char* src = (const char*)q.base + (size_t)(g0 - q.off) * q.row_bytes;
+            char* dst = P.base + poff + (size_t)(g0 - proff) * q.row_bytes;
+            PushSeg& sg = pa.seg[pa.count++];
+            sg.src = (const float4*)src; sg.dst = (float4*)dst; sg.n4 = (unsigned long long)q.n * q.row_bytes / 16;
+            total4 += sg.n4;
+        }
+    }
+    if (pa.count) {
+        const unsigned blocks = (unsigned)std::min<unsigned long long>((total4 / pa.count + 255) / 256, (unsigned long long)h->sm_count * 4);
+        halo_push_kernel<<<std::max(blocks, 1u), 256, 0, h->stream>>>(pa);
+        int rc = check_launch(h, "halo_push_kernel"); if (rc) return rc;
+    }
+    // (d) publish, (e) wait for the neighbours' rows
+    for (int side = 0; side < 2; ++side)
+        if (h->peer[side].present && M.write(h->stream, peer_flag(side, side == 0 ? 1 : 0), seq, 0))
+            return fail(h, FLUID_ERR_CUDA, "cuStreamWriteValue32 failed");
+    for (int side = 0; side < 2; ++side)
+        if (h->peer[side].present && M.wait(h->stream, my_flag(side == 0 ? 0 : 1), seq, 0))
+            return fail(h, FLUID_ERR_CUDA, "cuStreamWaitValue32 failed");
+    ++h->halo_groups;
+    return FLUID_OK;
+}
 
 int exchange_many(fluid_t* h, const HaloItem* it, int count) {
     if (!h->slab()) return FLUID_OK;
-    ncdl::Api& N = ncdl::api();
     for (int k = 0; k < count; ++k)
         if (it[k].n > it[k].r1 - it[k].r0)
             return fail(h, FLUID_ERR_HALO, "halo of %d rows exceeds the slab height %d (use fewer GPUs or a taller grid)",
                         it[k].n, it[k].r1 - it[k].r0);
+    if (h->p2p) return exchange_p2p(h, it, count);
+    ncdl::Api& N = ncdl::api();
     int rc = N.GroupStart();
     for (int k = 0; k < count && !rc; ++k) {
         const HaloItem& q = it[k];
@@ -150,8 +263,8 @@ int exchange_many(fluid_t* h, const HaloItem* it, int count) {
     return FLUID_OK;
 }
 
-int exchange_rows(fluid_t* h, void* base, size_t row_bytes, int off, int r0, int r1, int n) {
-    HaloItem it{base, row_bytes, off, r0, r1, n};
+int exchange_rows(fluid_t* h, int which, void* base, size_t row_bytes, int off, int r0, int r1, int n) {
+    HaloItem it{base, row_bytes, off, r0, r1, n, which};
     return exchange_many(h, &it, 1);
 }
 
@@ -228,7 +341,7 @@ int run_jacobi(fluid_t* h, int iters, bool scale_first, int* launches_out) {
             scale_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(
                 (const float*)h->pressure.read, (float*)h->pressure.write, n, h->cfg.pressure);
             int rc = check_launch(h, "scale_kernel"); if (rc) return rc;
-            h->pressure.swap(); ++nl;
+            swap_p(h); ++nl;
         }
         if (launches_out) *launches_out = nl;
         return FLUID_OK;
@@ -244,12 +357,12 @@ int run_jacobi(fluid_t* h, int iters, bool scale_first, int* launches_out) {
     const bool deep = h->slab() && (iters + 1 <= h->G) && (iters + 1 <= h->row1 - h->row0);
     if (h->slab()) {
         if (deep) {
-            HaloItem it[2] = {{h->pressure.read, (size_t)W * sizeof(float), h->roff, h->row0, h->row1, iters + 1},
-                              {h->divergence, (size_t)W * sizeof(float), h->roff, h->row0, h->row1, iters}};
+            HaloItem it[2] = {{h->pressure.read, (size_t)W * sizeof(float), h->roff, h->row0, h->row1, iters + 1, HB_PRESSURE},
+                              {h->divergence, (size_t)W * sizeof(float), h->roff, h->row0, h->row1, iters, HB_DIVERGENCE}};
             int rc = exchange_many(h, it, 2); if (rc) return rc;
         } else {
             const int kmax = base + (extra ? 1 : 0);
-            int rc = exchange_rows(h, h->divergence, (size_t)W * sizeof(float), h->roff, h->row0, h->row1, kmax);
+            int rc = exchange_rows(h, HB_DIVERGENCE, h->divergence, (size_t)W * sizeof(float), h->roff, h->row0, h->row1, kmax);
             if (rc) return rc;
         }
     }
@@ -266,7 +379,7 @@ int run_jacobi(fluid_t* h, int iters, bool scale_first, int* launches_out) {
                 ext = remaining + 1;
             } else {
                 ext = last ? 1 : 0;
-                int rc = exchange_rows(h, h->pressure.read, (size_t)W * sizeof(float), h->roff, h->row0, h->row1, K + ext);
+                int rc = exchange_rows(h, HB_PRESSURE, h->pressure.read, (size_t)W * sizeof(float), h->roff, h->row0, h->row1, K + ext);
                 if (rc) return rc;
             }
             a.out_lo = std::max(h->row0 - ext, 0); a.out_hi = std::min(h->row1 + ext, H);
@@ -287,7 +400,7 @@ int run_jacobi(fluid_t* h, int iters, bool scale_first, int* launches_out) {
             rc = check_launch(h, "jacobi_scalar_kernel");
         }
         if (rc) return rc;
-        h->pressure.swap(); ++nl;
+        swap_p(h); ++nl;
     }
     if (launches_out) *launches_out = nl;
     return FLUID_OK;
@@ -295,30 +408,55 @@ int run_jacobi(fluid_t* h, int iters, bool scale_first, int* launches_out) {
 
 int alloc_fields(fluid_t* h) {
     const size_t n = sim_cells(h), nd = dye_cells(h);
-    CU(cudaMalloc(&h->velocity.read, n * sizeof(float2)));
-    CU(cudaMalloc(&h->velocity.write, n * sizeof(float2)));
-    CU(cudaMalloc(&h->dye.read, nd * sizeof(float4)));
-    CU(cudaMalloc(&h->dye.write, nd * sizeof(float4)));
-    CU(cudaMalloc(&h->pressure.read, n * sizeof(float)));
-    CU(cudaMalloc(&h->pressure.write, n * sizeof(float)));
-    CU(cudaMalloc((void**)&h->divergence, n * sizeof(float)));
-    CU(cudaMalloc((void**)&h->curl, n * sizeof(float)));
-    CU(cudaMemsetAsync(h->velocity.read, 0, n * sizeof(float2), h->stream));
-    CU(cudaMemsetAsync(h->velocity.write, 0, n * sizeof(float2), h->stream));
-    CU(cudaMemsetAsync(h->pressure.read, 0, n * sizeof(float), h->stream));
-    CU(cudaMemsetAsync(h->pressure.write, 0, n * sizeof(float), h->stream));
-    CU(cudaMemsetAsync(h->divergence, 0, n * sizeof(float), h->stream));
-    CU(cudaMemsetAsync(h->curl, 0, n * sizeof(float), h->stream));
+    if (h->slab()) {
+        // one allocation, so that a single CUDA IPC handle maps everything a neighbour may write into
+        auto al = [](size_t b) { return (b + 1023) & ~(size_t)1023; };
+        size_t o = 0;
+        h->off_flags = o; o += 1024;
+        for (int k = 0; k < 2; ++k) { h->off_v[k] = o; o += al(n * sizeof(float2)); }
+        for (int k = 0; k < 2; ++k) { h->off_p[k] = o; o += al(n * sizeof(float)); }
+        for (int k = 0; k < 2; ++k) { h->off_dye[k] = o; o += al(nd * sizeof(float4)); }
+        h->off_div = o; o += al(n * sizeof(float));
+        const size_t off_curl = o; o += al(n * sizeof(float));
+        h->arena_bytes = o;
+        CU(cudaMalloc((void**)&h->arena, o));
+        CU(cudaMemsetAsync(h->arena, 0, o, h->stream));
+        h->velocity.read = h->arena + h->off_v[0]; h->velocity.write = h->arena + h->off_v[1];
+        h->pressure.read = h->arena + h->off_p[0]; h->pressure.write = h->arena + h->off_p[1];
+        h->dye.read = h->arena + h->off_dye[0]; h->dye.write = h->arena + h->off_dye[1];
+        h->divergence = (float*)(h->arena + h->off_div); h->curl = (float*)(h->arena + off_curl);
+        h->par_v = h->par_p = h->par_dye = 0;
+    } else {
+        CU(cudaMalloc(&h->velocity.read, n * sizeof(float2)));
+        CU(cudaMalloc(&h->velocity.write, n * sizeof(float2)));
+        CU(cudaMalloc(&h->dye.read, nd * sizeof(float4)));
+        CU(cudaMalloc(&h->dye.write, nd * sizeof(float4)));
+        CU(cudaMalloc(&h->pressure.read, n * sizeof(float)));
+        CU(cudaMalloc(&h->pressure.write, n * sizeof(float)));
+        CU(cudaMalloc((void**)&h->divergence, n * sizeof(float)));
+        CU(cudaMalloc((void**)&h->curl, n * sizeof(float)));
+        CU(cudaMemsetAsync(h->velocity.read, 0, n * sizeof(float2), h->stream));
+        CU(cudaMemsetAsync(h->velocity.write, 0, n * sizeof(float2), h->stream));
+        CU(cudaMemsetAsync(h->pressure.read, 0, n * sizeof(float), h->stream));
+        CU(cudaMemsetAsync(h->pressure.write, 0, n * sizeof(float), h->stream));
+        CU(cudaMemsetAsync(h->divergence, 0, n * sizeof(float), h->stream));
+        CU(cudaMemsetAsync(h->curl, 0, n * sizeof(float), h->stream));
+    }
     fill_alpha_kernel<<<(unsigned)((nd + 255) / 256), 256, 0, h->stream>>>((float4*)h->dye.read, nd);
     fill_alpha_kernel<<<(unsigned)((nd + 255) / 256), 256, 0, h->stream>>>((float4*)h->dye.write, nd);
     return check_launch(h, "fill_alpha_kernel", 2);
 }
 
 void free_fields(fluid_t* h) {
-    cudaFree(h->velocity.read); cudaFree(h->velocity.write);
-    cudaFree(h->dye.read); cudaFree(h->dye.write);
-    cudaFree(h->pressure.read); cudaFree(h->pressure.write);
-    cudaFree(h->divergence); cudaFree(h->curl);
+    if (h->arena) {
+        for (auto& p : h->peer) if (p.present && p.base) { cudaIpcCloseMemHandle(p.base); p.base = nullptr; p.present = false; }
+        cudaFree(h->arena); h->arena = nullptr;
+    } else {
+        cudaFree(h->velocity.read); cudaFree(h->velocity.write);
+        cudaFree(h->dye.read); cudaFree(h->dye.write);
+        cudaFree(h->pressure.read); cudaFree(h->pressure.write);
+        cudaFree(h->divergence); cudaFree(h->curl);
+    }
     h->velocity = Pair{}; h->dye = Pair{}; h->pressure = Pair{};
     h->divergence = h->curl = nullptr;
 }
@@ -484,6 +622,51 @@ int fluid_create_slab(const fluid_config* cfg, int rank, int world, const void* 
     return create_common(cfg, rank, world, nccl_uid, out);
 }
 
+// ---- peer-memory halo path -------------------------------------------------------------------------
+struct P2PBlob {            // what fluid_p2p_export hands to the launcher (opaque to it), 256 bytes
+    cudaIpcMemHandle_t mem;
+    int32_t rank, roff, droff, reserved;
+    uint64_t off_v[2], off_p[2], off_dye[2], off_div, off_flags, arena_bytes;
+    char pad[256 - sizeof(cudaIpcMemHandle_t) - 16 - 9 * 8];
+};
+static_assert(sizeof(P2PBlob) == 256, "blob layout");
+
+int fluid_p2p_export(fluid_t* h, void* blob, size_t blob_bytes) {
+    if (!h || !blob || blob_bytes < sizeof(P2PBlob)) return fail(h, FLUID_ERR_INVALID, "blob must hold 256 bytes");
+    if (!h->slab() || !h->arena) return fail(h, FLUID_ERR_INVALID, "fluid_p2p_export needs a slab handle");
+    P2PBlob b{};
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaIpcGetMemHandle(&b.mem, h->arena));
+    b.rank = h->rank; b.roff = h->roff; b.droff = h->droff;
+    for (int k = 0; k < 2; ++k) { b.off_v[k] = h->off_v[k]; b.off_p[k] = h->off_p[k]; b.off_dye[k] = h->off_dye[k]; }
+    b.off_div = h->off_div; b.off_flags = h->off_flags; b.arena_bytes = h->arena_bytes;
+    memcpy(blob, &b, sizeof b);
+    return FLUID_OK;
+}
+
+// blob_below / blob_above: the 256-byte exports of rank-1 / rank+1 (NULL at the domain ends).
+// Collective in spirit: every rank of the slab group must connect before the next fluid_step.
+int fluid_p2p_connect(fluid_t* h, const void* blob_below, const void* blob_above) {
+    if (!h || !h->slab() || !h->arena) return fail(h, FLUID_ERR_INVALID, "fluid_p2p_connect needs a slab handle");
+    if (!memops().ok) return fail(h, FLUID_ERR_CUDA, "cuStreamWriteValue32 / cuStreamWaitValue32 unavailable");
+    const void* blobs[2] = {blob_below, blob_above};
+    for (int side = 0; side < 2; ++side) {
+        const bool need = (side == 0) ? h->rank > 0 : h->rank + 1 < h->world;
+        if (!need) continue;
+        if (!blobs[side]) return fail(h, FLUID_ERR_INVALID, "missing neighbour blob (side %d)", side);
+        P2PBlob b; memcpy(&b, blobs[side], sizeof b);
+        if (b.rank != h->rank + (side == 0 ? -1 : 1)) return fail(h, FLUID_ERR_INVALID, "blob of rank %d passed as side %d of rank %d", b.rank, side, h->rank);
+        void* base = nullptr;
+        CU(cudaIpcOpenMemHandle(&base, b.mem, cudaIpcMemLazyEnablePeerAccess));
+        fluid::Peer& P = h->peer[side];
+        P.present = true; P.base = (char*)base; P.roff = b.roff; P.droff = b.droff;
+        for (int k = 0; k < 2; ++k) { P.off_v[k] = b.off_v[k]; P.off_p[k] = b.off_p[k]; P.off_dye[k] = b.off_dye[k]; }
+        P.off_div = b.off_div; P.off_flags = b.off_flags;
+    }
+    h->p2p = true;
+    return FLUID_OK;
+}
+
 void fluid_destroy(fluid_t* h) {
     if (!h) return;
     cudaSetDevice(h->device);
@@ -545,7 +728,7 @@ static int do_vorticity(fluid_t* h, Grid g, float dt) {
     vorticity_kernel<<<grid2d(g.W, g.j_hi - g.j_lo, b), b, 0, h->stream>>>(
         (const float2*)h->velocity.read, h->curl, (float2*)h->velocity.write, g, h->cfg.curl, dt);
     int rc = check_launch(h, "vorticity_kernel"); if (rc) return rc;
-    h->velocity.swap();                                   // S:1246
+    swap_v(h);                                   // S:1246
     return FLUID_OK;
 }
 static int do_divergence(fluid_t* h, Grid g) {
@@ -561,7 +744,7 @@ static int do_cvd(fluid_t* h, Grid g, float dt) {
         (const float2*)h->velocity.read, h->curl, (float2*)h->velocity.write, h->divergence, g,
         h->cfg.curl, dt);
     int rc = check_launch(h, "curl_vorticity_divergence_kernel"); if (rc) return rc;
-    h->velocity.swap();
+    swap_v(h);
     return FLUID_OK;
 }
 static int do_gradient(fluid_t* h, Grid g) {
@@ -569,7 +752,7 @@ static int do_gradient(fluid_t* h, Grid g) {
     gradient_subtract_kernel<<<grid2d(g.W, g.j_hi - g.j_lo, b), b, 0, h->stream>>>(
         (const float*)h->pressure.read, (const float2*)h->velocity.read, (float2*)h->velocity.write, g);
     int rc = check_launch(h, "gradient_subtract_kernel"); if (rc) return rc;
-    h->velocity.swap();                                   // S:1273
+    swap_v(h);                                   // S:1273
     return FLUID_OK;
 }
 // valid source rows of a slab buffer: owned + ghost, clipped to the domain
@@ -589,7 +772,7 @@ static int do_advect_velocity(fluid_t* h, Grid out, float dt) {
     else advect_velocity_kernel<false><<<grid2d(out.W, out.j_hi - out.j_lo, b), b, 0, h->stream>>>(
         (const float2*)h->velocity.read, (float2*)h->velocity.write, a);
     int rc = check_launch(h, "advect_velocity_kernel"); if (rc) return rc;
-    h->velocity.swap();                                   // S:1285
+    swap_v(h);                                   // S:1285
     return FLUID_OK;
 }
 static int do_advect_dye(fluid_t* h, float dt) {
@@ -608,7 +791,7 @@ static int do_advect_dye(fluid_t* h, float dt) {
     else if (p2) advect_dye_kernel<true, false><<<gr, b, 0, h->stream>>>(V, Dr, Dw, a);
     else advect_dye_kernel<false, false><<<gr, b, 0, h->stream>>>(V, Dr, Dw, a);
     int rc = check_launch(h, "advect_dye_kernel"); if (rc) return rc;
-    h->dye.swap();                                        // S:1293
+    swap_dye(h);                                        // S:1293
     return FLUID_OK;
 }
 
@@ -675,7 +858,7 @@ int fluid_step(fluid_t* h, float dt) {
     int jl = 0;
     if (timed) cudaEventRecord(h->tev[0], h->stream);
     if (h->slab() && !h->v_ghost_valid) {   // after fluid_write(velocity): rebuild the +-3 ghost rows
-        if ((rc = exchange_rows(h, h->velocity.read, (size_t)W * sizeof(float2), h->roff, h->row0, h->row1, 3))) return rc;
+        if ((rc = exchange_rows(h, HB_VELOCITY, h->velocity.read, (size_t)W * sizeof(float2), h->roff, h->row0, h->row1, 3))) return rc;
         h->v_ghost_valid = true;
     }
     if (h->cfg.flags & FLUID_FLAG_UNFUSED) {
@@ -691,12 +874,12 @@ int fluid_step(fluid_t* h, float dt) {
     if ((rc = do_gradient(h, sim_grid(h)))) return rc;
     if (timed) cudaEventRecord(h->tev[3], h->stream);
     if (h->slab()) {   // advection halo #1: G rows of the projected velocity
-        if ((rc = exchange_rows(h, h->velocity.read, (size_t)W * sizeof(float2), h->roff, h->row0, h->row1, h->G))) return rc;
+        if ((rc = exchange_rows(h, HB_VELOCITY, h->velocity.read, (size_t)W * sizeof(float2), h->roff, h->row0, h->row1, h->G))) return rc;
     }
     if ((rc = do_advect_velocity(h, sim_grid_ext(h, h->slab() ? 3 : 0), dt))) return rc;
     if (timed) cudaEventRecord(h->tev[4], h->stream);
     if (h->slab()) {   // advection halo #2: Gd rows of dye
-        if ((rc = exchange_rows(h, h->dye.read, (size_t)h->cfg.dye_w * sizeof(float4), h->droff, h->drow0, h->drow1, h->Gd))) return rc;
+        if ((rc = exchange_rows(h, HB_DYE, h->dye.read, (size_t)h->cfg.dye_w * sizeof(float4), h->droff, h->drow0, h->drow1, h->Gd))) return rc;
     }
     if ((rc = do_advect_dye(h, dt))) return rc;
     if (timed) cudaEventRecord(h->tev[5], h->stream);
@@ -720,11 +903,11 @@ int fluid_splat(fluid_t* h, float x, float y, float dx, float dy, float r, float
         (const float2*)h->velocity.read, (float2*)h->velocity.write, gs, h->cfg.aspect, x, y, dx, dy,
         radius);
     int rc = check_launch(h, "splat_velocity_kernel"); if (rc) return rc;
-    h->velocity.swap();                                   // S:1449
+    swap_v(h);                                   // S:1449
     splat_dye_kernel<<<grid2d(gd.W, gd.j_hi - gd.j_lo, bl), bl, 0, h->stream>>>(
         (const float4*)h->dye.read, (float4*)h->dye.write, gd, h->cfg.aspect, x, y, r, g, b, radius);
     rc = check_launch(h, "splat_dye_kernel"); if (rc) return rc;
-    h->dye.swap();                                        // S:1454
+    swap_dye(h);                                        // S:1454
     return FLUID_OK;
 }
 

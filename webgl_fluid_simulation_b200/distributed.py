@@ -3,6 +3,7 @@ broadcast of the ncclUniqueId); the halo exchange itself runs inside libfluid_b2
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 from . import _lib
 from .sim import FluidSimulation
@@ -22,5 +23,24 @@ def create_slab_simulation(config=None, canvas_width=1024, canvas_height=1024, d
     rank, world = dist.get_rank(), dist.get_world_size()
     box = [nccl_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(box, src=0)
-    return FluidSimulation(config, canvas_width, canvas_height, device=device, rank=rank, world=world,
-                           nccl_uid=box[0], **kw)
+    sim = FluidSimulation(config, canvas_width, canvas_height, device=device, rank=rank, world=world,
+                          nccl_uid=box[0], **kw)
+    if os.environ.get("FLUID_HALO", "p2p") != "nccl" and world > 1:
+        connect_peers(sim)
+    return sim
+
+
+def connect_peers(sim: FluidSimulation) -> None:
+    """Switch a slab handle to the peer-memory halo path: all-gather the 256-byte IPC exports and
+    connect each rank to rank-1 / rank+1 (single NVLink / NVSwitch box)."""
+    import torch.distributed as dist
+    L = _lib.lib()
+    rank, world = dist.get_rank(), dist.get_world_size()
+    blob = C.create_string_buffer(256)
+    sim._check(L.fluid_p2p_export(sim._h, blob, 256))
+    blobs = [None] * world
+    dist.all_gather_object(blobs, blob.raw)
+    below = C.create_string_buffer(blobs[rank - 1], 256) if rank > 0 else None
+    above = C.create_string_buffer(blobs[rank + 1], 256) if rank + 1 < world else None
+    sim._check(L.fluid_p2p_connect(sim._h, below, above))
+    dist.barrier()                                   # nobody pushes before everyone has mapped
