@@ -122,8 +122,9 @@ int fluid_nccl_unique_id(void* out_uid, size_t uid_bytes); /* uid_bytes must be 
 /* Optional peer-memory halo path for slab handles on one NVLink/NVSwitch box (no reference
  * counterpart).  Every rank exports a 256-byte blob (a CUDA IPC handle of its field arena + layout),
  * the launcher all-gathers them, and each rank connects to rank-1 / rank+1 (NULL at the ends).
- * Afterwards halo rows are pushed straight into the neighbours' ghost rows by one kernel and
- * ordered with stream memory operations; without it the NCCL send/recv path is used. */
+ * Afterwards halo rows are stored straight into the neighbours' ghost rows by one kernel that
+ * also carries the free/ready handshake (system-scope release/acquire flag words, bounded spins);
+ * without it the NCCL send/recv path is used. */
 int fluid_p2p_export(fluid_t* h, void* blob, size_t blob_bytes);   /* blob_bytes >= 256 */
 int fluid_p2p_connect(fluid_t* h, const void* blob_below, const void* blob_above);
 

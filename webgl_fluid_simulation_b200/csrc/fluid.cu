@@ -143,11 +143,50 @@ enum { HB_VELOCITY = 0, HB_PRESSURE = 1, HB_DYE = 2, HB_DIVERGENCE = 3 };
 struct HaloItem { void* base; size_t row_bytes; int off, r0, r1, n; int which; };
 
 struct PushSeg { const float4* src; float4* dst; unsigned long long n4; };
-struct PushArgs { PushSeg seg[8]; int count; };
+struct PushArgs {
+    PushSeg seg[8];
+    int count;
+    unsigned seq;
+    unsigned* my_flags;        // [0] ready-from-below [1] ready-from-above [2] free-from-below [3] free-from-above
+    unsigned* peer_flags[2];   // the same four words in the neighbours' arenas (IPC-mapped); [0] below, [1] above
+    int present[2];
+    unsigned* counter;         // block-completion counter (local)
+    int* err;                  // set when a bounded spin times out (reported as FLUID_ERR_HALO)
+};
 
-// Writes this rank's boundary rows straight into the neighbours' ghost rows: dst pointers are the
-// neighbours' buffers mapped through CUDA IPC, so the stores travel over NVLink / NVSwitch.
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t;
+}
+// bounded spin: a neighbour that never arrives costs 4 s and an error flag, never a hung GPU
+__device__ __forceinline__ void spin_until(const unsigned* flag, unsigned seq, int* err) {
+    const unsigned long long t0 = global_ns();
+    while ((int)(ld_acquire_sys(flag) - seq) < 0) {
+        if (global_ns() - t0 > 4000000000ull) { *err = 2; break; }
+        __nanosleep(100);
+    }
+}
+
+// The whole producer side of one halo exchange in ONE kernel:
+//   (a) tell the neighbours my ghost rows may be overwritten (this kernel is stream-ordered after
+//       every kernel of mine that read them), (b) wait until theirs are free, (c) store my boundary
+//       rows straight into their ghost rows — dst pointers are the neighbours' arenas mapped through
+//       CUDA IPC, so the stores travel over NVLink / NVSwitch — and (d) once the last block is
+//       done, release-store "ready = seq" into the neighbours' flag words.
 __global__ void __launch_bounds__(256) halo_push_kernel(PushArgs a) {
+    if (threadIdx.x == 0) {
+        if (blockIdx.x == 0)
+            for (int side = 0; side < 2; ++side)
+                if (a.present[side]) st_release_sys(a.peer_flags[side] + (side == 0 ? 3 : 2), a.seq);
+        for (int side = 0; side < 2; ++side)
+            if (a.present[side]) spin_until(a.my_flags + (side == 0 ? 2 : 3), a.seq, a.err);
+    }
+    __syncthreads();
     for (int k = 0; k < a.count; ++k) {
         const float4* __restrict__ s = a.seg[k].src;
         float4* __restrict__ d = a.seg[k].dst;
@@ -156,46 +195,38 @@ __global__ void __launch_bounds__(256) halo_push_kernel(PushArgs a) {
              i += (unsigned long long)gridDim.x * blockDim.x)
             d[i] = s[i];
     }
-}
-
-typedef int (*PFN_memop32)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
-struct MemOps { PFN_memop32 write = nullptr, wait = nullptr; bool ok = false; };
-MemOps& memops() {
-    static MemOps m;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        cudaDriverEntryPointQueryResult q;
-        void *w = nullptr, *t = nullptr;
-        if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &w, cudaEnableDefault, &q) == cudaSuccess && w &&
-            cudaGetDriverEntryPoint("cuStreamWaitValue32", &t, cudaEnableDefault, &q) == cudaSuccess && t) {
-            m.write = (PFN_memop32)w; m.wait = (PFN_memop32)t; m.ok = true;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned done = atomicAdd(a.counter, 1u);
+        if (done == gridDim.x - 1) {
+            *a.counter = 0;
+            __threadfence_system();
+            for (int side = 0; side < 2; ++side)
+                if (a.present[side]) st_release_sys(a.peer_flags[side] + (side == 0 ? 1 : 0), a.seq);
         }
     }
-    return m;
 }
 
-// flag words (uint32) at arena + off_flags:  [0] ready-from-below  [1] ready-from-above
-//                                            [2] free-from-below   [3] free-from-above
-// "ready" = the neighbour's rows for exchange `seq` have landed in my ghost rows;
-// "free"  = the neighbour has finished every kernel that read the ghost rows I fill, up to `seq`.
+// (e) consumer side: one thread acquires the neighbours' "ready" words; kernels after it in the
+// stream then read the ghost rows the neighbours stored.
+__global__ void halo_wait_kernel(const unsigned* my_flags, int present_below, int present_above,
+                                 unsigned seq, int* err) {
+    if (present_below) spin_until(my_flags + 0, seq, err);
+    if (present_above) spin_until(my_flags + 1, seq, err);
+}
+
 int exchange_p2p(fluid_t* h, const HaloItem* it, int count) {
-    MemOps& M = memops();
-    const uint32_t seq = ++h->p2p_seq;
-    auto my_flag = [&](int idx) { return (unsigned long long)(uintptr_t)(h->arena + h->off_flags + 4 * idx); };
-    auto peer_flag = [&](int side, int idx) { return (unsigned long long)(uintptr_t)(h->peer[side].base + h->peer[side].off_flags + 4 * idx); };
-    // (a) tell both neighbours that my ghost rows may be overwritten (stream-ordered after every
-    //     kernel of mine that read them); a neighbour BELOW me sees me as its ABOVE neighbour.
-    for (int side = 0; side < 2; ++side)
-        if (h->peer[side].present && M.write(h->stream, peer_flag(side, side == 0 ? 3 : 2), seq, 0))
-            return fail(h, FLUID_ERR_CUDA, "cuStreamWriteValue32 failed");
-    // (b) wait until their ghost rows are free
-    for (int side = 0; side < 2; ++side)
-        if (h->peer[side].present && M.wait(h->stream, my_flag(side == 0 ? 2 : 3), seq, 0 /* GEQ */))
-            return fail(h, FLUID_ERR_CUDA, "cuStreamWaitValue32 failed");
-    // (c) push
-    PushArgs pa{}; pa.count = 0;
+    PushArgs pa{};
+    pa.seq = ++h->p2p_seq;
+    pa.my_flags = (unsigned*)(h->arena + h->off_flags);
+    pa.counter = pa.my_flags + 8;
+    pa.err = h->halo_flag;
     unsigned long long total4 = 0;
+    for (int side = 0; side < 2; ++side) {
+        pa.present[side] = h->peer[side].present ? 1 : 0;
+        pa.peer_flags[side] = h->peer[side].present ? (unsigned*)(h->peer[side].base + h->peer[side].off_flags) : nullptr;
+    }
     for (int k = 0; k < count; ++k) {
         const HaloItem& q = it[k];
         if (q.n <= 0) continue;
@@ -212,23 +243,17 @@ int exchange_p2p(fluid_t* h, const HaloItem* it, int count) {
             const int g0 = (side == 1) ? q.r1 - q.n : q.r0;          // my owned rows that the neighbour needs
             const char* src = (const char*)q.base + (size_t)(g0 - q.off) * q.row_bytes;
             char* dst = P.base + poff + (size_t)(g0 - proff) * q.row_bytes;
+            if (pa.count >= 8) return fail(h, FLUID_ERR_INVALID, "too many halo segments");
             PushSeg& sg = pa.seg[pa.count++];
             sg.src = (const float4*)src; sg.dst = (float4*)dst; sg.n4 = (unsigned long long)q.n * q.row_bytes / 16;
-            total4 += sg.n4;
+            total4 = std::max(total4, sg.n4);
         }
     }
-    if (pa.count) {
-        const unsigned blocks = (unsigned)std::min<unsigned long long>((total4 / pa.count + 255) / 256, (unsigned long long)h->sm_count * 4);
-        halo_push_kernel<<<std::max(blocks, 1u), 256, 0, h->stream>>>(pa);
-        int rc = check_launch(h, "halo_push_kernel"); if (rc) return rc;
-    }
-    // (d) publish, (e) wait for the neighbours' rows
-    for (int side = 0; side < 2; ++side)
-        if (h->peer[side].present && M.write(h->stream, peer_flag(side, side == 0 ? 1 : 0), seq, 0))
-            return fail(h, FLUID_ERR_CUDA, "cuStreamWriteValue32 failed");
-    for (int side = 0; side < 2; ++side)
-        if (h->peer[side].present && M.wait(h->stream, my_flag(side == 0 ? 0 : 1), seq, 0))
-            return fail(h, FLUID_ERR_CUDA, "cuStreamWaitValue32 failed");
+    const unsigned blocks = (unsigned)std::min<unsigned long long>(std::max<unsigned long long>((total4 + 255) / 256, 1), (unsigned long long)h->sm_count * 2);
+    halo_push_kernel<<<blocks, 256, 0, h->stream>>>(pa);
+    int rc = check_launch(h, "halo_push_kernel"); if (rc) return rc;
+    halo_wait_kernel<<<1, 1, 0, h->stream>>>(pa.my_flags, pa.present[0], pa.present[1], pa.seq, pa.err);
+    rc = check_launch(h, "halo_wait_kernel"); if (rc) return rc;
     ++h->halo_groups;
     return FLUID_OK;
 }
@@ -481,6 +506,8 @@ int check_halo(fluid_t* h) {
     int flag = 0;
     CU(cudaMemcpyAsync(&flag, h->halo_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    if (flag == 2)
+        return fail(h, FLUID_ERR_HALO, "peer-memory halo exchange timed out waiting for a neighbour rank");
     if (flag)
         return fail(h, FLUID_ERR_HALO, "advection back-trace left the %d-row ghost zone: |v|*dt exceeds it; "
                     "re-create the slab handle with a taller halo (FLUID_HALO_ROWS)", h->G);
@@ -648,7 +675,6 @@ int fluid_p2p_export(fluid_t* h, void* blob, size_t blob_bytes) {
 // Collective in spirit: every rank of the slab group must connect before the next fluid_step.
 int fluid_p2p_connect(fluid_t* h, const void* blob_below, const void* blob_above) {
     if (!h || !h->slab() || !h->arena) return fail(h, FLUID_ERR_INVALID, "fluid_p2p_connect needs a slab handle");
-    if (!memops().ok) return fail(h, FLUID_ERR_CUDA, "cuStreamWriteValue32 / cuStreamWaitValue32 unavailable");
     const void* blobs[2] = {blob_below, blob_above};
     for (int side = 0; side < 2; ++side) {
         const bool need = (side == 0) ? h->rank > 0 : h->rank + 1 < h->world;
