@@ -156,12 +156,20 @@ def run_reference(args, rank, world):
     }))
 
 
-def time_steps(sim, fn, steps):
+HOST_MS = {}
+
+
+def time_steps(sim, fn, steps, tag=None):
     sim.mark(0)
+    t0 = time.perf_counter()
     for _ in range(steps):
         fn()
+    host = time.perf_counter() - t0          # enqueue time only: if it approaches the device time the run is host-bound
     sim.mark(1)
-    return sim.elapsed_ms()
+    ms = sim.elapsed_ms()
+    if tag:
+        HOST_MS[tag] = 1e3 * host / steps
+    return ms
 
 
 def main():
@@ -215,7 +223,7 @@ def main():
         solve()
     barrier()
     with ClockSampler(local) as clk:
-        ms = time_steps(sim, solve, args.steps)
+        ms = time_steps(sim, solve, args.steps, tag="solve")
         sim.sync()
         # keep the device loaded until NVML has a few samples even if the timed region is short
         # (single GPU only: on slabs every solve is a collective, so all ranks must issue the
@@ -266,6 +274,7 @@ def main():
                    "parallelism": "single GPU" if world == 1 else
                    f"{world} row slabs of {W}x{H} (global grid {W}x{H * world}), NCCL halo exchange of p/div rows per blocked launch"},
         "clocks": clk.summary(), "gpu_launches": gpu_launches, "roofline": roofline,
+        "host_enqueue_ms_per_step": HOST_MS.get("solve"),
     }
 
     if args.quick:

@@ -152,6 +152,7 @@ struct PushArgs {
     int present[2];
     unsigned* counter;         // block-completion counter (local)
     int* err;                  // set when a bounded spin times out (reported as FLUID_ERR_HALO)
+    unsigned long long* dbg;   // FLUID_DEBUG_HALO_TIMING: [0] sum wait-free ns [1] sum push ns [2] sum wait-ready ns [3] count [4] t_start
 };
 
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
@@ -180,11 +181,15 @@ __device__ __forceinline__ void spin_until(const unsigned* flag, unsigned seq, i
 //       done, release-store "ready = seq" into the neighbours' flag words.
 __global__ void __launch_bounds__(256) halo_push_kernel(PushArgs a) {
     if (threadIdx.x == 0) {
-        if (blockIdx.x == 0)
+        unsigned long long t0 = 0;
+        if (blockIdx.x == 0) {
+            if (a.dbg) { t0 = global_ns(); a.dbg[4] = t0; }
             for (int side = 0; side < 2; ++side)
                 if (a.present[side]) st_release_sys(a.peer_flags[side] + (side == 0 ? 3 : 2), a.seq);
+        }
         for (int side = 0; side < 2; ++side)
             if (a.present[side]) spin_until(a.my_flags + (side == 0 ? 2 : 3), a.seq, a.err);
+        if (blockIdx.x == 0 && a.dbg) atomicAdd(a.dbg + 0, global_ns() - t0);
     }
     __syncthreads();
     for (int k = 0; k < a.count; ++k) {
@@ -204,6 +209,7 @@ __global__ void __launch_bounds__(256) halo_push_kernel(PushArgs a) {
             __threadfence_system();
             for (int side = 0; side < 2; ++side)
                 if (a.present[side]) st_release_sys(a.peer_flags[side] + (side == 0 ? 1 : 0), a.seq);
+            if (a.dbg) { atomicAdd(a.dbg + 1, global_ns() - a.dbg[4]); atomicAdd(a.dbg + 3, 1ull); }
         }
     }
 }
@@ -211,9 +217,11 @@ __global__ void __launch_bounds__(256) halo_push_kernel(PushArgs a) {
 // (e) consumer side: one thread acquires the neighbours' "ready" words; kernels after it in the
 // stream then read the ghost rows the neighbours stored.
 __global__ void halo_wait_kernel(const unsigned* my_flags, int present_below, int present_above,
-                                 unsigned seq, int* err) {
+                                 unsigned seq, int* err, unsigned long long* dbg) {
+    const unsigned long long t0 = dbg ? global_ns() : 0;
     if (present_below) spin_until(my_flags + 0, seq, err);
     if (present_above) spin_until(my_flags + 1, seq, err);
+    if (dbg) atomicAdd(dbg + 2, global_ns() - t0);
 }
 
 int exchange_p2p(fluid_t* h, const HaloItem* it, int count) {
@@ -222,6 +230,8 @@ int exchange_p2p(fluid_t* h, const HaloItem* it, int count) {
     pa.my_flags = (unsigned*)(h->arena + h->off_flags);
     pa.counter = pa.my_flags + 8;
     pa.err = h->halo_flag;
+    static const bool dbg = getenv("FLUID_DEBUG_HALO_TIMING") != nullptr;
+    pa.dbg = dbg ? (unsigned long long*)(h->arena + h->off_flags + 128) : nullptr;
     unsigned long long total4 = 0;
     for (int side = 0; side < 2; ++side) {
         pa.present[side] = h->peer[side].present ? 1 : 0;
@@ -252,7 +262,7 @@ int exchange_p2p(fluid_t* h, const HaloItem* it, int count) {
     const unsigned blocks = (unsigned)std::min<unsigned long long>(std::max<unsigned long long>((total4 + 255) / 256, 1), (unsigned long long)h->sm_count * 2);
     halo_push_kernel<<<blocks, 256, 0, h->stream>>>(pa);
     int rc = check_launch(h, "halo_push_kernel"); if (rc) return rc;
-    halo_wait_kernel<<<1, 1, 0, h->stream>>>(pa.my_flags, pa.present[0], pa.present[1], pa.seq, pa.err);
+    halo_wait_kernel<<<1, 1, 0, h->stream>>>(pa.my_flags, pa.present[0], pa.present[1], pa.seq, pa.err, pa.dbg);
     rc = check_launch(h, "halo_wait_kernel"); if (rc) return rc;
     ++h->halo_groups;
     return FLUID_OK;
@@ -264,6 +274,8 @@ int exchange_many(fluid_t* h, const HaloItem* it, int count) {
         if (it[k].n > it[k].r1 - it[k].r0)
             return fail(h, FLUID_ERR_HALO, "halo of %d rows exceeds the slab height %d (use fewer GPUs or a taller grid)",
                         it[k].n, it[k].r1 - it[k].r0);
+    static const bool skip = getenv("FLUID_DEBUG_SKIP_HALO") != nullptr;   // TIMING EXPERIMENTS ONLY: wrong results
+    if (skip) return FLUID_OK;
     if (h->p2p) return exchange_p2p(h, it, count);
     ncdl::Api& N = ncdl::api();
     int rc = N.GroupStart();
@@ -697,6 +709,12 @@ void fluid_destroy(fluid_t* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->p2p && getenv("FLUID_DEBUG_HALO_TIMING")) {
+        unsigned long long d[5] = {};
+        cudaMemcpy(d, h->arena + h->off_flags + 128, sizeof d, cudaMemcpyDeviceToHost);
+        if (d[3]) fprintf(stderr, "[halo rank %d] exchanges %llu: wait-free %.1f us, push (start->published) %.1f us, wait-ready %.1f us\n",
+                          h->rank, d[3], d[0] / 1e3 / d[3], d[1] / 1e3 / d[3], d[2] / 1e3 / d[3]);
+    }
     free_fields(h);
     cudaFree(h->halo_flag);
     if (h->comm) { ncdl::api().CommDestroy(h->comm); h->comm = nullptr; }
