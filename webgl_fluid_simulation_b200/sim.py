@@ -177,6 +177,14 @@ class FluidSimulation:
             cfg.dye_w, cfg.dye_h = dyeRes["width"], dyeRes["height"]
             cfg.aspect = self._aspect()
             cfg.device, cfg.flags, cfg.jacobi_block = self._device, self._flags, self._jb
+            # the simulation keys as they stand now (a slab handle sizes its ghost zone from
+            # PRESSURE_ITERATIONS); later changes are pushed live by _push_config()
+            cfg.density_dissipation = float(self.config["DENSITY_DISSIPATION"])
+            cfg.velocity_dissipation = float(self.config["VELOCITY_DISSIPATION"])
+            cfg.pressure = float(self.config["PRESSURE"])
+            cfg.pressure_iterations = int(self.config["PRESSURE_ITERATIONS"])
+            cfg.curl = float(self.config["CURL"])
+            cfg.splat_radius = float(self.config["SPLAT_RADIUS"])
             if self._world > 1:
                 uid = C.create_string_buffer(self._uid, len(self._uid))
                 self._check(self._L.fluid_create_slab(C.byref(cfg), self._rank, self._world, uid,
