@@ -109,36 +109,44 @@ def synth_inputs(seed=42):
     return p, d
 
 
-def cpu_port_rate(budget_s=12.0, cap=100000):
+def cpu_port_rate(budget_s=12.0):
     """CPU restatement of the pressure loop (oracle/, OpenMP, all host cores) on a bounded sample."""
+    import ctypes as C
     from oracle import oracle as O
+    L = O.lib()
     p, d = synth_inputs()
-    O.jacobi(p, d, 1)                                   # warm-up, page in
-    t0 = time.perf_counter(); O.jacobi(p, d, 2); t1 = time.perf_counter()
-    per = (t1 - t0) / 2
-    n = int(max(2, min(cap, budget_s / max(per, 1e-6))))
+    tmp = np.empty_like(p)
+    fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+    L.oracle_jacobi_iters(fp(p), fp(tmp), fp(d), W, H, 2)          # warm-up, page in
     t0 = time.perf_counter(); done = 0
-    while True:                                          # the calibration above can be cold: run to the budget
-        O.jacobi(p, d, n); done += n
+    while True:
+        L.oracle_jacobi_iters(fp(p), fp(tmp), fp(d), W, H, 10); done += 10
         dt = time.perf_counter() - t0
-        if dt >= 0.8 * budget_s:
+        if dt >= budget_s:
             break
-    n = done
-    return (W * H * n / dt, O.num_threads(),
-            f"{n} Jacobi sweeps of {W}x{H} fp32 (= {n / ITERS:.1f} x the {ITERS}-sweep solve), {dt:.1f} s of CPU time")
+    return (W * H * done / dt, O.num_threads(),
+            f"{done} Jacobi sweeps of {W}x{H} fp32 (= {done / ITERS:.1f} x the {ITERS}-sweep solve), {dt:.1f} s of CPU time")
 
 
 def run_reference(args, rank, world):
+    """Reference arm: the reference's own WebGL path cannot run here, so this is the CPU
+    restatement of its pressure loop (oracle/, C + OpenMP, every host core) on the same inputs.
+    Each step is a bounded sample: SWEEPS Jacobi sweeps of the 50-sweep solve, on preallocated
+    buffers (no per-step allocation or copies in the timed region)."""
     if rank != 0:
         return
+    import ctypes as C
     from oracle import oracle as O
+    L = O.lib()
     p, d = synth_inputs()
-    sweeps = 3                                           # bounded sample per step
+    tmp = np.empty_like(p)
+    fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+    sweeps = 10                                          # bounded sample per step (even: result lands back in p)
     for _ in range(max(args.warmup, 1)):
-        O.jacobi(p, d, 1)
+        L.oracle_jacobi_iters(fp(p), fp(tmp), fp(d), W, H, 2)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        O.jacobi(p, d, sweeps)
+        L.oracle_jacobi_iters(fp(p), fp(tmp), fp(d), W, H, sweeps)
     dt = time.perf_counter() - t0
     val = W * H * sweeps * args.steps / dt
     sample = f"each step = {sweeps} Jacobi sweeps of {W}x{H} fp32 out of the {ITERS}-sweep solve"
