@@ -341,6 +341,18 @@ def main():
                          "launches_per_step": tm["total_launches"]}
             s2.close()
         out["full_step"] = ctx
+        # ---- the reference's own default config (launch-bound regime): graph replay vs pass by pass ----
+        dflt = {}
+        for tag, fl in (("cuda_graph", 0), ("pass_by_pass", pkg.FLAG_NO_GRAPH)):
+            s3 = pkg.FluidSimulation({}, 1024, 1024, device=local, flags=fl, random=np.random.RandomState(7).random_sample)
+            s3.multipleSplats(8)
+            for _ in range(5): s3.step(0.016666)
+            n3 = 200
+            m3 = time_steps(s3, lambda: s3.step(0.016666), n3); s3.sync()
+            dflt[tag] = {"ms_per_step": m3 / n3}
+            s3.close()
+        out["default_config_step"] = {"config": "128x128 sim / 1024x1024 dye, 20 iters (script.js defaults, S:59-69)", **dflt,
+                                      "reference_draw_calls_per_step": 27, "kernels_per_step": 6}
 
         if not args.no_cpu:
             v, cores, sample = cpu_port_rate()

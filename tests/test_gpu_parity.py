@@ -224,3 +224,29 @@ def test_live_config_and_error_paths(pkg):
         s.set_param("CURL", 1.0) or s._check(s._L.fluid_set_param(s._h, 99, 0.0))
     assert s.launch_count() > 0
     s.close()
+
+
+def test_graph_replay_equals_pass_by_pass(pkg):
+    """fluid_step as a cached CUDA graph (default) == the same step launched kernel by kernel
+    (FLUID_FLAG_NO_GRAPH), bit for bit, across cache misses (new dt, changed config, both
+    ping-pong parities) and hits; writes and splats between steps must be seen by the replays."""
+    W = H = 128; Wd = Hd = 256
+    v, dye, p = rand_fields(W, H, Wd, Hd, 21)
+    sims = [make(pkg, W, H, Wd, Hd, flags=f) for f in (0, pkg.FLAG_NO_GRAPH)]
+    for s in sims:
+        s.writeField("velocity", v); s.writeField("dye", dye); s.writeField("pressure", p)
+    dts = [0.016666, 0.016666, 0.016666, 0.01, 0.016666, 0.01, 0.016666, 0.016666]
+    for k, dt in enumerate(dts):
+        for s in sims:
+            if k == 3:
+                s.config["CURL"] = 12.5
+            if k == 5:
+                s.splat(0.4, 0.7, 200.0, -100.0, (0.3, 0.6, 0.9))
+            if k == 6:
+                s.config["PRESSURE_ITERATIONS"] = 33
+            s.step(dt)
+    for n in ("velocity", "dye", "pressure", "divergence", "curl"):
+        assert bits_equal(sims[0].readField(n), sims[1].readField(n)), n
+    assert sims[0].launch_count() == sims[1].launch_count()
+    for s in sims:
+        s.close()

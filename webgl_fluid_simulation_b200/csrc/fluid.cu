@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -73,6 +74,10 @@ struct fluid {
     } peer[2];                       // [0] = rank-1 (below), [1] = rank+1 (above)
     bool p2p = false;
     uint32_t p2p_seq = 0;
+    // ---- step() as a CUDA graph (single GPU): one instantiated graph per (dt, config scalars, parity)
+    struct StepGraph { cudaGraphExec_t exec = nullptr; int flip_v = 0, flip_p = 0, flip_dye = 0, kernels = 0, jacobi_launches = 0; };
+    std::map<std::string, StepGraph> graphs;
+    uint64_t graph_launches = 0, graph_captures = 0;
     bool slab() const { return world > 1; }
     int lrows() const { return row1 - row0 + 2 * G; }
     int ldrows() const { return drow1 - drow0 + 2 * Gd; }
@@ -85,6 +90,11 @@ using namespace fk;
 inline void swap_v(fluid_t* h) { h->velocity.swap(); h->par_v ^= 1; }
 inline void swap_p(fluid_t* h) { h->pressure.swap(); h->par_p ^= 1; }
 inline void swap_dye(fluid_t* h) { h->dye.swap(); h->par_dye ^= 1; }
+
+void drop_graphs(fluid_t* h) {
+    for (auto& kv : h->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    h->graphs.clear();
+}
 
 int fail(fluid_t* h, int code, const char* fmt, ...) {
     char buf[512];
@@ -709,6 +719,7 @@ void fluid_destroy(fluid_t* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    drop_graphs(h);
     if (h->p2p && getenv("FLUID_DEBUG_HALO_TIMING")) {
         unsigned long long d[5] = {};
         cudaMemcpy(d, h->arena + h->off_flags + 128, sizeof d, cudaMemcpyDeviceToHost);
@@ -893,10 +904,8 @@ int fluid_pass_advect_dye(fluid_t* h, float dt) {
 // halos below; curl / vorticity / divergence / gradientSubtract read ghost rows that the previous
 // step's advection (velocity on owned rows +- 3) and the last Jacobi launch (pressure on owned
 // rows +- 1) already computed redundantly.
-int fluid_step(fluid_t* h, float dt) {
-    if (!h) return FLUID_ERR_INVALID;
+static int step_enqueue(fluid_t* h, float dt, bool timed) {
     const uint64_t l0 = h->launches;
-    const bool timed = (h->cfg.flags & FLUID_FLAG_NO_GRAPH) != 0;
     const int W = h->cfg.sim_w;
     int rc;
     int jl = 0;
@@ -933,6 +942,56 @@ int fluid_step(fluid_t* h, float dt) {
     return FLUID_OK;
 }
 
+// The reference pays one draw call per pass (7 + PRESSURE_ITERATIONS per step) and is bound by
+// that at its default 128^2 grid.  Here a step is 4 + ceil(iters/10) kernels, and on a single GPU
+// they are replayed as ONE instantiated CUDA graph.  A graph bakes in kernel arguments, so the
+// cache key holds everything they depend on: dt, the config scalars, the grid sizes and which
+// half of each ping-pong pair is currently `.read`.
+int fluid_step(fluid_t* h, float dt) {
+    if (!h) return FLUID_ERR_INVALID;
+    const bool no_graph = (h->cfg.flags & FLUID_FLAG_NO_GRAPH) != 0;
+    if (no_graph || h->slab()) return step_enqueue(h, dt, no_graph);
+    char key[256];
+    const fluid_config& c = h->cfg;
+    snprintf(key, sizeof key, "%08x|%a|%a|%a|%a|%d|%d|%u|%d%d%d|%dx%d|%dx%d", *reinterpret_cast<const unsigned*>(&dt),
+             c.curl, c.pressure, c.velocity_dissipation, c.density_dissipation, c.pressure_iterations, c.jacobi_block,
+             c.flags, h->par_v, h->par_p, h->par_dye, c.sim_w, c.sim_h, c.dye_w, c.dye_h);
+    auto it = h->graphs.find(key);
+    if (it == h->graphs.end()) {
+        if (h->graphs.size() > 64) drop_graphs(h);          // dt that never repeats: do not grow without bound
+        const int pv = h->par_v, pp = h->par_p, pd = h->par_dye;
+        const uint64_t l0 = h->launches;
+        cudaGraph_t g = nullptr;
+        CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = step_enqueue(h, dt, false);
+        cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+        if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+        if (e != cudaSuccess) return fail(h, FLUID_ERR_CUDA, "stream capture of step() failed: %s", cudaGetErrorString(e));
+        fluid::StepGraph sg;
+        e = cudaGraphInstantiate(&sg.exec, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) return fail(h, FLUID_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+        sg.flip_v = pv ^ h->par_v; sg.flip_p = pp ^ h->par_p; sg.flip_dye = pd ^ h->par_dye;
+        sg.kernels = (int)(h->launches - l0); sg.jacobi_launches = h->timing.jacobi_launches;
+        h->launches = l0;                                    // captured, not yet executed
+        ++h->graph_captures;
+        it = h->graphs.emplace(key, sg).first;
+        // the capture already performed the host-side swaps of this step
+    } else {
+        const fluid::StepGraph& sg = it->second;
+        if (sg.flip_v) swap_v(h);
+        if (sg.flip_p) swap_p(h);
+        if (sg.flip_dye) swap_dye(h);
+    }
+    CU(cudaGraphLaunch(it->second.exec, h->stream));
+    h->launches += it->second.kernels;
+    h->timing.jacobi_launches = it->second.jacobi_launches;
+    h->timing.total_launches = it->second.kernels;
+    h->have_timing = false;
+    ++h->graph_launches;
+    return FLUID_OK;
+}
+
 // splat(x,y,dx,dy,color), S:1441-1455
 int fluid_splat(fluid_t* h, float x, float y, float dx, float dy, float r, float g, float b) {
     if (!h) return FLUID_ERR_INVALID;
@@ -960,6 +1019,8 @@ int fluid_resize(fluid_t* h, int sim_w, int sim_h, int dye_w, int dye_h) {
     if (!h) return FLUID_ERR_INVALID;
     if (sim_w < 1 || sim_h < 1 || dye_w < 1 || dye_h < 1) return fail(h, FLUID_ERR_INVALID, "bad size");
     if (h->slab()) return not_on_slab(h, "fluid_resize");
+    CU(cudaStreamSynchronize(h->stream));
+    drop_graphs(h);                                          // graphs hold the old buffers' addresses
     const int ow = h->cfg.sim_w, oh = h->cfg.sim_h, odw = h->cfg.dye_w, odh = h->cfg.dye_h;
     dim3 b(64, 4);
     const size_t n = (size_t)sim_w * sim_h, nd = (size_t)dye_w * dye_h;
