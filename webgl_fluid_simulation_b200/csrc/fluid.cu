@@ -324,7 +324,10 @@ int launch_tb(fluid_t* h, const JacobiArgs& a) {
     using T = TB<K>;
     const int nxw = (a.W + T::VALID - 1) / T::VALID;
     const int nch = (a.out_hi - a.out_lo + a.rows_per_chunk - 1) / a.rows_per_chunk;
-    jacobi_tb_kernel<K, SCALE><<<nxw * nch, 32, T::SMEM, h->stream>>>(a);   // one warp per CTA
+    // staging fill: TMA bulk copies (default) or per-lane LDGSTS (FLUID_TB_STAGE=ldgsts)
+    static const bool tma = !(getenv("FLUID_TB_STAGE") && !strcmp(getenv("FLUID_TB_STAGE"), "ldgsts"));
+    if (tma) jacobi_tb_kernel<K, SCALE, true><<<nxw * nch, 32, T::SMEM, h->stream>>>(a);   // one warp per CTA
+    else jacobi_tb_kernel<K, SCALE, false><<<nxw * nch, 32, T::SMEM, h->stream>>>(a);
     return check_launch(h, "jacobi_tb_kernel");
 }
 
@@ -341,7 +344,7 @@ int tb_rows(const fluid_t* h, int W, int rows) {
     using T = TB<K>;
     const int nxw = (W + T::VALID - 1) / T::VALID;
     int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, jacobi_tb_kernel<K, false>, 32, T::SMEM);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, jacobi_tb_kernel<K, false, true>, 32, T::SMEM);
     if (occ < 1) occ = 1;
     const int resident_warps = h->sm_count * occ;
     const int nch = std::max(1, resident_warps / nxw);
@@ -378,6 +381,7 @@ int run_jacobi(fluid_t* h, int iters, bool scale_first, int* launches_out) {
     JacobiArgs a{};
     a.div = h->divergence; a.W = W; a.H = H; a.row_off = h->roff; a.out_lo = h->row0; a.out_hi = h->row1;
     a.scale = h->cfg.pressure;
+    a.err = h->halo_flag;
     int kb = h->cfg.jacobi_block > 0 ? h->cfg.jacobi_block : 10;  // tuned on B200: profiles/r01_tune_jacobi.txt
     kb = std::min(kb, KMAX);
     if (h->slab()) kb = std::max(1, std::min(kb, h->G - 1));
@@ -524,12 +528,13 @@ int field_info(const fluid_t* h, int field, void** ptr, int* w, int* rows, int* 
 // Multi-GPU: an advection back-trace that needed a row outside the ghost zone set the device flag;
 // never clamp silently — report it at the next synchronisation point.
 int check_halo(fluid_t* h) {
-    if (!h->slab()) return FLUID_OK;   // single GPU: taps are always clamped in-grid
     int flag = 0;
     CU(cudaMemcpyAsync(&flag, h->halo_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     if (flag == 2)
         return fail(h, FLUID_ERR_HALO, "peer-memory halo exchange timed out waiting for a neighbour rank");
+    if (flag == 3)
+        return fail(h, FLUID_ERR_CUDA, "jacobi_tb_kernel: a TMA staging barrier never completed");
     if (flag)
         return fail(h, FLUID_ERR_HALO, "advection back-trace left the %d-row ghost zone: |v|*dt exceeds it; "
                     "re-create the slab handle with a taller halo (FLUID_HALO_ROWS)", h->G);
@@ -953,7 +958,8 @@ int fluid_step(fluid_t* h, float dt) {
     if (no_graph || h->slab()) return step_enqueue(h, dt, no_graph);
     char key[256];
     const fluid_config& c = h->cfg;
-    snprintf(key, sizeof key, "%08x|%a|%a|%a|%a|%d|%d|%u|%d%d%d|%dx%d|%dx%d", *reinterpret_cast<const unsigned*>(&dt),
+    unsigned dtb; memcpy(&dtb, &dt, sizeof dtb);
+    snprintf(key, sizeof key, "%08x|%a|%a|%a|%a|%d|%d|%u|%d%d%d|%dx%d|%dx%d", dtb,
              c.curl, c.pressure, c.velocity_dissipation, c.density_dissipation, c.pressure_iterations, c.jacobi_block,
              c.flags, h->par_v, h->par_p, h->par_dye, c.sim_w, c.sim_h, c.dye_w, c.dye_h);
     auto it = h->graphs.find(key);

@@ -21,9 +21,10 @@
 //       explicitly (EDGE instantiation, only on the few steps that touch those rows);
 //     * div[r] is needed by level t when it produces row r, i.e. K times at K different steps:
 //       each lane keeps its float4 of the last K+3 rows in a register ring (see tb_block);
-//     * p / div rows are staged D rows ahead with cp.async (LDGSTS, 16 B per lane, coalesced
-//       512 B per warp row segment) into a per-warp shared-memory ring each lane reads back
-//       itself, so the few resident warps still keep enough bytes in flight for HBM.
+//     * p / div rows are staged D rows ahead into a per-warp shared-memory ring, so the few
+//       resident warps still keep enough bytes in flight for HBM.  Two interchangeable fills:
+//       TMA — one elected lane issues cp.async.bulk (UBLKCP) of the window's 512 B row segment
+//       with mbarrier complete_tx; or LDGSTS — every lane cp.asyncs its own 16 B.
 //   The optional SCALE template fuses the clear pass (S:1253-1257, p <- PRESSURE*p) into the
 //   level-0 load of the first launch: one fp32 multiply, same rounding as the separate blit.
 #pragma once
@@ -41,6 +42,7 @@ struct JacobiArgs {
     int out_lo, out_hi;  // global rows [out_lo, out_hi) to produce
     int rows_per_chunk;  // tb kernel: output rows per warp stream
     float scale;         // SCALE: value of config.PRESSURE
+    int* err;            // device error word (3 = a bounded mbarrier wait gave up)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -107,7 +109,7 @@ struct TB {
     static constexpr int RD = K + 3;                 // div register-ring slots
     static constexpr int U = 3;                      // pipeline steps per unrolled block
     static constexpr int D = 8;                      // staging depth: rows in flight per stream
-    static constexpr int SMEM = D * 2 * 32 * (int)sizeof(float4);   // p + div staging rings
+    static constexpr int SMEM = D * 2 * 32 * (int)sizeof(float4) + D * 8;   // p + div staging rings + D mbarriers
 };
 
 // ---- cp.async (LDGSTS) staging: global -> shared without passing through registers ------------
@@ -120,6 +122,37 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// ---- cp.async.bulk (1-D TMA, SASS UBLKCP) + mbarrier: the TMA variant of the same staging ring -----
+// One elected lane arms the slot's mbarrier with the byte count and issues two bulk copies (the p
+// and div row segments of this window, 512 B each away from the walls); the hardware completes the
+// barrier when the bytes have landed.  Waits are bounded: a mis-armed barrier costs an error word,
+// never a hung kernel.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(void* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, void* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(void* bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(void* bar, unsigned parity, int* err) {
+    if (mbar_try_wait(bar, parity)) return;              // the common case: the row landed long ago
+#pragma unroll 1
+    for (int tries = 0; tries < (1 << 16); ++tries)      // each try_wait already blocks for a HW time slice
+        if (mbar_try_wait(bar, parity)) return;
+    if (err) *err = 3;
+}
+
 __device__ __forceinline__ float4 lds128(const float4* p) {
     float4 v;
     const unsigned a = (unsigned)__cvta_generic_to_shared(p);
@@ -185,6 +218,20 @@ struct TBStream {
     int rload;           // global row index pl/dl point at
     int rout;            // global row index op points at  (= ys + s - K)
     int slot;            // staging slot consumed at this step (0..D-1)
+    // TMA variant only
+    unsigned phase;      // mbarrier parity of the slot consumed at this step
+    const float* pseg;   // next p row: first in-domain column of this window (warp-uniform)
+    const float* dseg;   // next div row, ditto
+};
+
+struct TBSeg {           // the part of a window's 128 columns that lies inside the grid (TMA variant)
+    unsigned bytes;      // (ce - cs) * 4, a multiple of 16
+    int dst4;            // float4 index of column cs inside a slot ((cs - x0) / 4)
+    int W;               // row pitch in floats
+    unsigned long long* bars;   // D mbarriers
+    float4* slots;       // smem4 base (slot q of p at slots + q*32, of div at slots + (D+q)*32)
+    int lane;
+    int* err;
 };
 
 // One unrolled block of 3 pipeline steps.
@@ -200,23 +247,41 @@ struct TBStream {
 //     flight per stream give the memory-level parallelism the few resident warps cannot.
 // EDGE instantiates the wall selects in y, REV the mirrored-lane reversal in x; both are chosen
 // by warp-uniform branches OUTSIDE the steady-state loop.
-template <int K, bool SCALE, bool EDGE, bool REV>
+template <int K, bool SCALE, bool EDGE, bool REV, bool TMA>
 __device__ __forceinline__ void tb_block(float4 (&w)[K][3], float4 (&dr)[TB<K>::RD], TBStream& st,
-                                         float4* __restrict__ ring, const int W4, const int ye,
-                                         const int y0, const int y1, const int H, const bool rev,
-                                         const bool lane_out, const float scale) {
+                                         float4* __restrict__ ring, const TBSeg& sg, const int W4,
+                                         const int ye, const int y0, const int y1, const int H,
+                                         const bool rev, const bool lane_out, const float scale) {
     using T = TB<K>;
 #pragma unroll
     for (int ph = 0; ph < 3; ++ph) {
-        // ---- level 0: wait for the oldest staged row, read it, refill its slot --------------------
-        cp_async_wait<T::D - 1>();
-        float4 in = lds128(st.stage);
-        float4 dv = lds128(st.stage + T::D * 32);
-        cp_async16(st.stage, st.pl);
-        cp_async16(st.stage + T::D * 32, st.dl);
-        cp_async_commit();
-        if (st.rload < ye) { ++st.rload; st.pl += W4; st.dl += W4; }   // loads clamp to row ye
-        st.slot = (st.slot + 1 == T::D) ? 0 : st.slot + 1;
+        // ---- level 0: wait for the oldest staged row, read it, refill a slot ----------------------
+        float4 in, dv;
+        if (TMA) {
+            mbar_wait(sg.bars + st.slot, st.phase, sg.err);
+            in = lds128(st.stage);
+            dv = lds128(st.stage + T::D * 32);
+            // refill the slot consumed ONE STEP AGO (its values have been used, so every lane's
+            // reads of it have completed); D-1 rows stay in flight
+            __syncwarp();
+            if (sg.lane == 0) {
+                const int t = (st.slot == 0) ? T::D - 1 : st.slot - 1;
+                mbar_expect_tx(sg.bars + t, 2 * sg.bytes);
+                bulk_g2s(sg.slots + t * 32 + sg.dst4, st.pseg, sg.bytes, sg.bars + t);
+                bulk_g2s(sg.slots + (T::D + t) * 32 + sg.dst4, st.dseg, sg.bytes, sg.bars + t);
+            }
+            if (st.rload < ye) { ++st.rload; st.pseg += sg.W; st.dseg += sg.W; }
+            if (st.slot + 1 == T::D) { st.slot = 0; st.phase ^= 1u; } else { ++st.slot; }
+        } else {
+            cp_async_wait<T::D - 1>();
+            in = lds128(st.stage);
+            dv = lds128(st.stage + T::D * 32);
+            cp_async16(st.stage, st.pl);
+            cp_async16(st.stage + T::D * 32, st.dl);
+            cp_async_commit();
+            if (st.rload < ye) { ++st.rload; st.pl += W4; st.dl += W4; }   // loads clamp to row ye
+            st.slot = (st.slot + 1 == T::D) ? 0 : st.slot + 1;
+        }
         st.stage = ring + st.slot * 32;
         if (REV) { in = rev4(in, rev); dv = rev4(dv, rev); }
         if (SCALE) {
@@ -250,9 +315,9 @@ __device__ __forceinline__ void tb_block(float4 (&w)[K][3], float4 (&dr)[TB<K>::
     for (int j = 0; j < K; ++j) dr[j] = dr[j + 3];
 }
 
-template <int K, bool SCALE, bool REV>
-__device__ __forceinline__ void tb_stream(const JacobiArgs& a, float4* __restrict__ ring,
-                                          const int lc, const int gx, const bool rev,
+template <int K, bool SCALE, bool REV, bool TMA>
+__device__ __forceinline__ void tb_stream(const JacobiArgs& a, float4* __restrict__ smem4, const int lane,
+                                          const int x0, const int lc, const int gx, const bool rev,
                                           const bool lane_out, const int cy) {
     using T = TB<K>;
     const int W = a.W, H = a.H, W4 = W >> 2;
@@ -264,8 +329,6 @@ __device__ __forceinline__ void tb_stream(const JacobiArgs& a, float4* __restric
     const int nsteps = y1 - ys + K;                   // level K emits row ys+s-K at step s
 
     const ptrdiff_t base = -(ptrdiff_t)a.row_off * W4;
-    const float4* Pg = reinterpret_cast<const float4*>(a.pin) + base + (lc >> 2);
-    const float4* Dg = reinterpret_cast<const float4*>(a.div) + base + (lc >> 2);
     float4* Og = reinterpret_cast<float4*>(a.pout) + base + (lane_out ? (gx >> 2) : 0);
 
     // rotating windows: w[t][(ph+0)%3] = row r-1, [(ph+1)%3] = row r, [(ph+2)%3] = fresh row r+1
@@ -278,19 +341,58 @@ __device__ __forceinline__ void tb_stream(const JacobiArgs& a, float4* __restric
 #pragma unroll
     for (int q = 0; q < T::RD; ++q) dr[q] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    // fill the staging ring: rows ys .. ys+D-1 (clamped to ye), one cp.async group per row
     TBStream st;
+    TBSeg sg{};
+    float4* ring;
     st.rload = ys;
-    st.pl = Pg + (ptrdiff_t)ys * W4;
-    st.dl = Dg + (ptrdiff_t)ys * W4;
-#pragma unroll
-    for (int q = 0; q < T::D; ++q) {
-        cp_async16(ring + q * 32, st.pl);
-        cp_async16(ring + (T::D + q) * 32, st.dl);
-        cp_async_commit();
-        if (st.rload < ye) { ++st.rload; st.pl += W4; st.dl += W4; }
-    }
     st.slot = 0;
+    st.phase = 0;
+    if (TMA) {
+        // the window's in-grid column segment [cs, ce); every lane reads its (mirrored / clamped)
+        // column group out of the staged segment
+        const int cs = max(x0, 0), ce = min(x0 + 128, W);
+        const int lcs = min(max(lc, cs), ce - 4);
+        sg.bytes = (unsigned)(ce - cs) * 4u;
+        sg.dst4 = (cs - x0) >> 2;
+        sg.W = W;
+        sg.bars = reinterpret_cast<unsigned long long*>(smem4 + 2 * T::D * 32);
+        sg.slots = smem4;
+        sg.lane = lane;
+        sg.err = a.err;
+        ring = smem4 + ((lcs - x0) >> 2);
+        st.pseg = a.pin + ((ptrdiff_t)ys - a.row_off) * W + cs;
+        st.dseg = a.div + ((ptrdiff_t)ys - a.row_off) * W + cs;
+        if (lane == 0) {
+#pragma unroll
+            for (int q = 0; q < T::D; ++q) mbar_init(sg.bars + q, 1);
+            mbar_fence_init();
+        }
+        __syncwarp();
+        // fill slots 0 .. D-2 with rows ys .. ys+D-2 (clamped to ye); slot D-1 is filled at step 0
+#pragma unroll
+        for (int q = 0; q < T::D - 1; ++q) {
+            if (lane == 0) {
+                mbar_expect_tx(sg.bars + q, 2 * sg.bytes);
+                bulk_g2s(sg.slots + q * 32 + sg.dst4, st.pseg, sg.bytes, sg.bars + q);
+                bulk_g2s(sg.slots + (T::D + q) * 32 + sg.dst4, st.dseg, sg.bytes, sg.bars + q);
+            }
+            if (st.rload < ye) { ++st.rload; st.pseg += W; st.dseg += W; }
+        }
+    } else {
+        ring = smem4 + lane;                          // p slot q at ring[q*32], div at ring[(D+q)*32]
+        const float4* Pg = reinterpret_cast<const float4*>(a.pin) + base + (lc >> 2);
+        const float4* Dg = reinterpret_cast<const float4*>(a.div) + base + (lc >> 2);
+        st.pl = Pg + (ptrdiff_t)ys * W4;
+        st.dl = Dg + (ptrdiff_t)ys * W4;
+        // fill the staging ring: rows ys .. ys+D-1 (clamped to ye), one cp.async group per row
+#pragma unroll
+        for (int q = 0; q < T::D; ++q) {
+            cp_async16(ring + q * 32, st.pl);
+            cp_async16(ring + (T::D + q) * 32, st.dl);
+            cp_async_commit();
+            if (st.rload < ye) { ++st.rload; st.pl += W4; st.dl += W4; }
+        }
+    }
     st.stage = ring;
     st.rout = ys - K;
     st.op = Og + (ptrdiff_t)st.rout * W4;             // only dereferenced for rows in [y0, y1)
@@ -304,21 +406,30 @@ __device__ __forceinline__ void tb_stream(const JacobiArgs& a, float4* __restric
     for (int part = 0; part < 2; ++part) {
 #pragma unroll 1
         for (; s0 < nsteps && ((ys + s0 - K <= 0) || (ys + s0 + 2 >= H - 1)); s0 += 3)
-            tb_block<K, SCALE, true, REV>(w, dr, st, ring, W4, ye, y0, y1, H, rev, lane_out, a.scale);
+            tb_block<K, SCALE, true, REV, TMA>(w, dr, st, ring, sg, W4, ye, y0, y1, H, rev, lane_out, a.scale);
 #pragma unroll 1
         for (; s0 < nsteps && !((ys + s0 - K <= 0) || (ys + s0 + 2 >= H - 1)); s0 += 3)
-            tb_block<K, SCALE, false, REV>(w, dr, st, ring, W4, ye, y0, y1, H, rev, lane_out, a.scale);
+            tb_block<K, SCALE, false, REV, TMA>(w, dr, st, ring, sg, W4, ye, y0, y1, H, rev, lane_out, a.scale);
     }
-    cp_async_wait<0>();                               // drain the over-fetched tail before exit
+    // drain the over-fetched tail before the CTA (and its shared memory) goes away
+    if (TMA) {
+#pragma unroll 1
+        for (int q = 0; q < T::D - 1; ++q) {
+            mbar_wait(sg.bars + st.slot, st.phase, sg.err);
+            if (st.slot + 1 == T::D) { st.slot = 0; st.phase ^= 1u; } else { ++st.slot; }
+        }
+    } else {
+        cp_async_wait<0>();
+    }
 }
 
 // One warp per CTA: every quantity that steers control flow derives from blockIdx and kernel
 // arguments only, so the compiler can prove the warp converged at each shuffle (no WARPSYNC /
 // BSSY scaffolding) and keeps loop state in uniform registers.
-template <int K, bool SCALE>
+template <int K, bool SCALE, bool TMA>
 __global__ void __launch_bounds__(32) jacobi_tb_kernel(JacobiArgs a) {
     using T = TB<K>;
-    extern __shared__ float4 smem4[];
+    extern __shared__ __align__(16) float4 smem4[];
     const int lane = threadIdx.x;
     const int nxw = (a.W + T::VALID - 1) / T::VALID;
     const int wid = blockIdx.x;
@@ -334,9 +445,9 @@ __global__ void __launch_bounds__(32) jacobi_tb_kernel(JacobiArgs a) {
     lc = min(max(lc, 0), W - 4);
     const bool any_rev = (wx == 0) || ((wx + 1) * T::VALID + T::HX > W);   // warp-uniform
     const bool lane_out = (lane >= T::HX / 4) && (lane < 32 - T::HX / 4) && (gx >= 0) && (gx < W);
-    float4* ring = smem4 + lane;                      // p slot q at ring[q*32], div at ring[(D+q)*32]
-    if (any_rev) tb_stream<K, SCALE, true>(a, ring, lc, gx, rev, lane_out, cy);
-    else tb_stream<K, SCALE, false>(a, ring, lc, gx, rev, lane_out, cy);
+    const int x0 = wx * T::VALID - T::HX;
+    if (any_rev) tb_stream<K, SCALE, true, TMA>(a, smem4, lane, x0, lc, gx, rev, lane_out, cy);
+    else tb_stream<K, SCALE, false, TMA>(a, smem4, lane, x0, lc, gx, rev, lane_out, cy);
 }
 
 }  // namespace fk
