@@ -324,8 +324,10 @@ int launch_tb(fluid_t* h, const JacobiArgs& a) {
     using T = TB<K>;
     const int nxw = (a.W + T::VALID - 1) / T::VALID;
     const int nch = (a.out_hi - a.out_lo + a.rows_per_chunk - 1) / a.rows_per_chunk;
-    // staging fill: TMA bulk copies (default) or per-lane LDGSTS (FLUID_TB_STAGE=ldgsts)
-    static const bool tma = !(getenv("FLUID_TB_STAGE") && !strcmp(getenv("FLUID_TB_STAGE"), "ldgsts"));
+    // staging fill: per-lane LDGSTS (default) or TMA bulk copies (FLUID_TB_STAGE=tma).  Measured on
+    // B200 at 4096^2 x 50: LDGSTS 0.287 ms, TMA 0.330 ms — a 512 B row segment per warp is too small
+    // for the elected-lane + mbarrier handshake to pay (profiles/r01_tma_vs_ldgsts.txt).
+    static const bool tma = getenv("FLUID_TB_STAGE") && !strcmp(getenv("FLUID_TB_STAGE"), "tma");
     if (tma) jacobi_tb_kernel<K, SCALE, true><<<nxw * nch, 32, T::SMEM, h->stream>>>(a);   // one warp per CTA
     else jacobi_tb_kernel<K, SCALE, false><<<nxw * nch, 32, T::SMEM, h->stream>>>(a);
     return check_launch(h, "jacobi_tb_kernel");
