@@ -271,6 +271,14 @@ def main():
         "note": "temporal blocking runs several sweeps per launch out of registers, so the "
                 "12 B/update algorithmic figure exceeds what DRAM actually moves; frac > 1 is "
                 "expected; compulsory_frac counts 12 B/cell once per launch",
+        # what actually bounds the blocked kernel (ncu: FMA pipe ~62 % busy, DRAM ~40 %): 5 fp32 ops
+        # per update on the 128-lane/SM fp32 pipes, each op issued as FADD/FADD2/FMUL2 (no FMA: the
+        # reference expression rounds after every add)
+        "fp32_pipe": {"ops_per_update": 5,
+                      "achieved_tops": 5 * W * H * ITERS * args.steps / (ms * 1e-3) / 1e12,
+                      "peak_tops": 148 * 128 * ((clk.summary().get("sm_mhz") or 1965.0) * 1e6) / 1e12,
+                      "frac": (5 * W * H * ITERS * args.steps / (ms * 1e-3)) / (148 * 128 * ((clk.summary().get("sm_mhz") or 1965.0) * 1e6)),
+                      "note": "useful updates only; overlapped tiling recomputes ~1.3x of them (x halo 12/128, y warm-up 2K rows per chunk)"},
     }
 
     out = {

@@ -250,3 +250,22 @@ def test_graph_replay_equals_pass_by_pass(pkg):
     assert sims[0].launch_count() == sims[1].launch_count()
     for s in sims:
         s.close()
+
+
+def test_random_shapes_blocked_jacobi_vs_oracle(pkg, oracle):
+    """Randomised sweep (seeded) over grid shapes, iteration counts and block depths: widths that
+    are / are not multiples of 4 and of the 104..120-column window payload, 1-row and 2-row grids,
+    depths 1..12.  Every case bitwise against the oracle, fused clear included."""
+    O = oracle
+    rng = np.random.default_rng(2024)
+    for case in range(40):
+        W = int(rng.choice([rng.integers(1, 40), 4 * rng.integers(4, 160), rng.integers(16, 700)]))
+        H = int(rng.choice([1, 2, rng.integers(3, 40), rng.integers(40, 300)]))
+        iters = int(rng.integers(1, 45)); jb = int(rng.integers(1, 13))
+        p = rng.standard_normal((H, W)).astype(np.float32)
+        d = rng.uniform(-1, 1, (H, W)).astype(np.float32)
+        s = make(pkg, W, H, 8, 8, jb=jb, PRESSURE_ITERATIONS=iters)
+        s.writeField("pressure", p); s.writeField("divergence", d)
+        s.pass_("pressure_solve")
+        got = s.readField("pressure"); s.close()
+        assert bits_equal(got, O.jacobi(O.clear(p, 0.8), d, iters)), (case, W, H, iters, jb)
