@@ -181,6 +181,14 @@ int fluid_write(fluid_t* h, int field, const float* host, size_t n_floats);
 int fluid_pressure_solve_host(fluid_t* h, const float* div_host, float* pressure_host_inout,
                               int iters);
 
+/* The consumer on the far side of the path ("next" row of SURVEY §8f, partially built):
+ * render(target) of S:1296-1317 with config.BLOOM = config.SUNRAYS = false and TRANSPARENT = false —
+ * drawColor(BACK_COLOR) (S:1319-1323) then drawDisplay (S:1331-1348, displayShaderSource S:549-612,
+ * SHADING keyword when `shading` != 0) blended ONE / ONE_MINUS_SRC_ALPHA.  Writes width*height RGBA
+ * floats (row 0 = bottom, not yet quantised to 8 bits) to host memory.  back_* are BACK_COLOR / 255. */
+int fluid_render(fluid_t* h, int width, int height, int shading, float back_r, float back_g,
+                 float back_b, float* host_rgba, size_t n_floats);
+
 int fluid_sync(fluid_t* h);
 int fluid_timing_last(fluid_t* h, fluid_timing* out);
 

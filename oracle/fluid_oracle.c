@@ -241,6 +241,62 @@ void oracle_resample(const float* src, int Ws, int Hs, float* dst, int Wd, int H
     }
 }
 
+/* GL_LINEAR + CLAMP_TO_EDGE fetch as the GL ES 2.0 spec (3.7.7) writes it: u' = u*W - 0.5,
+ * i0 = floor(u'), alpha = frac(u'); tau = (1-a)(1-b) t00 + a(1-b) t10 + (1-a) b t01 + a b t11. */
+static inline void linear_fetch(const float* tex, int W, int H, int C, float uvx, float uvy, float* out) {
+    const float u = uvx * (float)W - 0.5f, v = uvy * (float)H - 0.5f;
+    const float fi = floorf(u), fj = floorf(v);
+    const float a = u - fi, b = v - fj;
+    const int i0 = texel_index(fi, W), i1 = texel_index(fi + 1.0f, W);
+    const int j0 = texel_index(fj, H), j1 = texel_index(fj + 1.0f, H);
+    const float w00 = (1.0f - a) * (1.0f - b), w10 = a * (1.0f - b), w01 = (1.0f - a) * b, w11 = a * b;
+    const float* t00 = tex + ((size_t)j0 * W + i0) * C; const float* t10 = tex + ((size_t)j0 * W + i1) * C;
+    const float* t01 = tex + ((size_t)j1 * W + i0) * C; const float* t11 = tex + ((size_t)j1 * W + i1) * C;
+    for (int k = 0; k < C; ++k) out[k] = ((w00 * t00[k] + w10 * t10[k]) + w01 * t01[k]) + w11 * t11[k];
+}
+
+/* render(target) with BLOOM and SUNRAYS off, TRANSPARENT off (S:1296-1317): drawColor(BACK_COLOR)
+ * (S:1319-1323, colorShader S:521-529) then drawDisplay (S:1331-1348, displayShaderSource
+ * S:549-612 with the SHADING keyword when `shading`), blended ONE / ONE_MINUS_SRC_ALPHA (S:1305).
+ * dye is sampled through its LINEAR filter at the target's resolution w x h; out is w*h RGBA. */
+void oracle_display(const float* dye, int Wd, int Hd, float* out, int w, int h, int shading,
+                    const float* back_rgb) {
+    const float tsx = (float)(1.0 / (double)w), tsy = (float)(1.0 / (double)h);   /* S:1337 */
+#pragma omp parallel for schedule(static)
+    for (int j = 0; j < h; ++j) {
+        const float uvy = ((float)j + 0.5f) / (float)h;
+        for (int i = 0; i < w; ++i) {
+            const float uvx = ((float)i + 0.5f) / (float)w;
+            float c[4];
+            linear_fetch(dye, Wd, Hd, 4, uvx, uvy, c);
+            if (shading) {
+                float lc[4], rc[4], tc[4], bc[4];
+                linear_fetch(dye, Wd, Hd, 4, uvx - tsx, uvy, lc);
+                linear_fetch(dye, Wd, Hd, 4, uvx + tsx, uvy, rc);
+                linear_fetch(dye, Wd, Hd, 4, uvx, uvy + tsy, tc);
+                linear_fetch(dye, Wd, Hd, 4, uvx, uvy - tsy, bc);
+#define LEN3(v) sqrtf(((v)[0] * (v)[0] + (v)[1] * (v)[1]) + (v)[2] * (v)[2])
+                const float dx = LEN3(rc) - LEN3(lc);
+                const float dy = LEN3(tc) - LEN3(bc);
+                const float nz = sqrtf(tsx * tsx + tsy * tsy);               /* length(texelSize) */
+                const float nl = sqrtf((dx * dx + dy * dy) + nz * nz);       /* normalize = v / length(v) */
+                const float n2 = nz / nl;
+                /* dot(n, vec3(0,0,1)) = n.x*0 + n.y*0 + n.z*1 */
+                const float d = ((dx / nl) * 0.0f + (dy / nl) * 0.0f) + n2 * 1.0f;
+                const float diffuse = fminf(fmaxf(d + 0.7f, 0.7f), 1.0f);
+                c[0] = c[0] * diffuse; c[1] = c[1] * diffuse; c[2] = c[2] * diffuse;
+            }
+            const float a = fmaxf(c[0], fmaxf(c[1], c[2]));
+            float* o = out + ((size_t)j * w + i) * 4;
+            const float k = 1.0f - a;                                        /* ONE_MINUS_SRC_ALPHA */
+            o[0] = c[0] + back_rgb[0] * k;
+            o[1] = c[1] + back_rgb[1] * k;
+            o[2] = c[2] + back_rgb[2] * k;
+            o[3] = a + 1.0f * k;
+        }
+    }
+}
+
 void oracle_round_half(float* a, size_t n) {
 #pragma omp parallel for schedule(static)
     for (long long k = 0; k < (long long)n; ++k) a[k] = (float)(_Float16)a[k];

@@ -47,6 +47,10 @@ void oracle_splat(const float* base, float* out, int W, int H, int C, float aspe
 /* copyShader S:496-506 through a LINEAR sampler, as resizeFBO S:1108-1114 uses it */
 void oracle_resample(const float* src, int Ws, int Hs, float* dst, int Wd, int Hd, int C);
 
+/* render() without post-FX: drawColor + drawDisplay (S:1296-1348, displayShaderSource S:549-612) */
+void oracle_display(const float* dye, int Wd, int Hd, float* out, int w, int h, int shading,
+                    const float* back_rgb);
+
 /* fp16 storage emulation (S:138-147, S:986-1006): round every element through IEEE half, RNE */
 void oracle_round_half(float* a, size_t n);
 

@@ -140,6 +140,17 @@ def g_max(a, b):
     return np.maximum(a, b)
 
 
+def g_normalize(a): return V(a.arr / g_length(a)[..., None])        # v / length(v)
+
+
+def g_clamp(x, lo, hi): return g_min(g_max(x, lo), hi)              # min(max(x, lo), hi)
+
+
+def g_pow(x, y):
+    if isinstance(x, V): return V(np.power(x.arr, x._co(y)).astype(F))
+    return np.power(x, y).astype(F)
+
+
 def g_where(c, a, b):
     if isinstance(a, V) or isinstance(b, V):
         aa = a.arr if isinstance(a, V) else a
@@ -218,8 +229,11 @@ def g_texture2D(sam, uv):
 
 
 def extract_shader(js: str, name: str):
-    """Source + keyword list of `const <name> = compileShader(gl.X_SHADER, `...`[, keywords]);`"""
+    """Source of `const <name> = compileShader(gl.X_SHADER, `...`[, keywords]);` or of a plain
+    template-string constant (`const displayShaderSource = `...`;`, compiled later by Material)."""
     m = re.search(r"const\s+" + re.escape(name) + r"\s*=\s*compileShader\(\s*gl\.\w+,\s*`(.*?)`", js, re.S)
+    if not m:
+        m = re.search(r"const\s+" + re.escape(name) + r"\s*=\s*`(.*?)`", js, re.S)
     if not m:
         raise KeyError(name)
     return m.group(1)
@@ -243,7 +257,7 @@ def _preprocess(src: str, defines):
 _TYPES = r"(?:float|vec2|vec3|vec4|int|bool)"
 _RENAME = {"texture2D": "g_texture2D", "mix": "g_mix", "dot": "g_dot", "length": "g_length",
            "min": "g_min", "max": "g_max", "floor": "g_floor", "fract": "g_fract", "exp": "g_exp",
-           "abs": "g_abs"}
+           "abs": "g_abs", "normalize": "g_normalize", "clamp": "g_clamp", "pow": "g_pow"}
 
 
 def _expr(e: str) -> str:
@@ -343,7 +357,8 @@ class Program:
         base = {"vec2": _vecn(2), "vec3": _vecn(3), "vec4": _vecn(4), "g_texture2D": g_texture2D,
                 "g_mix": g_mix, "g_dot": g_dot, "g_length": g_length, "g_min": g_min,
                 "g_max": g_max, "g_floor": _map(_floor), "g_fract": _map(_fract),
-                "g_exp": _map(np.exp), "g_abs": _map(np.abs), "g_where": g_where, "g_copy": g_copy}
+                "g_exp": _map(np.exp), "g_abs": _map(np.abs), "g_where": g_where, "g_copy": g_copy,
+                "g_normalize": g_normalize, "g_clamp": g_clamp, "g_pow": g_pow}
         self.vs_env = dict(base); exec(self.vs_src, self.vs_env)
         self.fs_env = dict(base); exec(self.fs_src, self.fs_env)
         self.u = {}
@@ -483,6 +498,27 @@ class GLSLSim:
         sp.blit(self.velocity.write); self.velocity.swap()
         sp.set(uTarget=self.dye.read, color=tuple(color))
         sp.blit(self.dye.write); self.dye.swap()
+
+    def render(self, width, height, shading=True, back_color=(0, 0, 0)):
+        """render(target) with config.BLOOM = config.SUNRAYS = false, TRANSPARENT = false
+        (S:1296-1317): drawColor(normalizeColor(BACK_COLOR)) then drawDisplay, blended
+        ONE / ONE_MINUS_SRC_ALPHA (S:1305).  Returns the (height, width, 4) float target."""
+        js = open(REFERENCE_JS).read()
+        target = Texture(width, height, 4, True)
+        color = Program(js, "baseVertexShader", "colorShader")
+        color.set(texelSize=(1.0 / width, 1.0 / height),
+                  color=(back_color[0] / 255, back_color[1] / 255, back_color[2] / 255, 1))   # S:1321, S:1599
+        color.blit(target)
+        dst = target.data.copy()
+        disp = Program(js, "baseVertexShader", "displayShaderSource", ("SHADING",) if shading else ())
+        # the dye texture is sampled through its LINEAR filter here whatever the advection path was
+        dye = Texture(self.dye.read.w, self.dye.read.h, 4, True)
+        dye.data = self.dye.read.data
+        disp.set(texelSize=(1.0 / width, 1.0 / height), uTexture=dye)                      # S:1337-1338
+        disp.blit(target)
+        src = target.data
+        one_minus_a = (F(1.0) - src[..., 3:4]).astype(F)
+        return (src + dst * one_minus_a).astype(F)                                          # S:1305
 
     # numpy views in this repo's array conventions
     def fields(self):

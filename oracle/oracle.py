@@ -48,6 +48,7 @@ def lib():
         L.oracle_splat.argtypes = [_f, _f, i, i, i, f, f, f, _f, f]
         L.oracle_resample.argtypes = [_f, i, i, _f, i, i, i]
         L.oracle_round_half.argtypes = [_f, sz]
+        L.oracle_display.argtypes = [_f, i, i, _f, i, i, i, _f]; L.oracle_display.restype = None
         L.oracle_num_threads.restype = i
         for fn in (L.oracle_curl, L.oracle_vorticity, L.oracle_divergence, L.oracle_clear,
                    L.oracle_jacobi, L.oracle_jacobi_iters, L.oracle_gradient_subtract,
@@ -135,6 +136,15 @@ def resample(src, Wd, Hd):
     src = _c(src); Hs, Ws, Cc = src.shape
     out = np.empty((Hd, Wd, Cc), np.float32)
     lib().oracle_resample(_p(src), Ws, Hs, _p(out), Wd, Hd, Cc)
+    return out
+
+
+def display(dye, w, h, shading=True, back_rgb=(0.0, 0.0, 0.0)):
+    """render() with bloom / sunrays off: (h, w, 4) float RGBA, row 0 = bottom."""
+    dye = _c(dye); Hd, Wd, _ = dye.shape
+    out = np.empty((h, w, 4), np.float32)
+    back = np.asarray(back_rgb, np.float32)
+    lib().oracle_display(_p(dye), Wd, Hd, _p(out), w, h, 1 if shading else 0, _p(back))
     return out
 
 

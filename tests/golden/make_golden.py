@@ -92,7 +92,21 @@ def scenario(name, W, H, Wd, Hd, nsplat, steps, config, seed, **kw):
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **o)
 
 
+def display(name, Wd, Hd, w, h, seed):
+    """render() with bloom / sunrays off: executed colorShader + displayShaderSource, blended."""
+    rng = np.random.default_rng(seed)
+    s = G.GLSLSim(16, 16, Wd, Hd)
+    dye = (rng.random((Hd, Wd, 4), dtype=np.float32) * 2).astype(np.float32); dye[..., 3] = 1
+    s.load(dye=dye)
+    o = dict(Wd=Wd, Hd=Hd, w=w, h=h, in_dye=dye, back=np.array([30, 60, 200], np.float32))
+    o["shaded"] = s.render(w, h, True, (30, 60, 200))
+    o["flat"] = s.render(w, h, False, (30, 60, 200))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **o)
+
+
 if __name__ == "__main__":
+    display("display_64_to_128", 64, 64, 128, 128, 11)      # power-of-two target: bitwise
+    display("display_40x28_to_50x30", 40, 28, 50, 30, 12)   # ragged: vUv rounding -> tolerance
     per_pass(32, 32, 64, 64, 1)
     per_pass(24, 16, 40, 28, 2)      # non-square, non-power-of-two, Wd/W not integer
     per_pass(64, 32, 128, 64, 3)

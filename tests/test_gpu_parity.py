@@ -269,3 +269,30 @@ def test_random_shapes_blocked_jacobi_vs_oracle(pkg, oracle):
         s.pass_("pressure_solve")
         got = s.readField("pressure"); s.close()
         assert bits_equal(got, O.jacobi(O.clear(p, 0.8), d, iters)), (case, W, H, iters, jb)
+
+
+@pytest.mark.parametrize("Wd,Hd,w,h", [(64, 64, 128, 128), (40, 28, 50, 30), (256, 256, 333, 200)])
+def test_render_display_bitwise_vs_oracle(pkg, oracle, Wd, Hd, w, h):
+    """The display pass ("next" row): fluid_render == the oracle bit for bit, shaded and flat, and
+    equals the executed-reference golden on the power-of-two case."""
+    rng = np.random.default_rng(Wd + w)
+    dye = (rng.random((Hd, Wd, 4), dtype=np.float32) * 2).astype(np.float32); dye[..., 3] = 1
+    s = make(pkg, 16, 16, Wd, Hd)
+    s.writeField("dye", dye)
+    s.config["BACK_COLOR"] = {"r": 30, "g": 60, "b": 200}
+    for shading in (True, False):
+        s.config["SHADING"] = shading
+        got = s.render(w, h)
+        assert bits_equal(got, oracle.display(dye, w, h, shading, (30 / 255, 60 / 255, 200 / 255))), shading
+    img = s.textureToCanvas(got)
+    assert img.dtype == np.uint8 and img.shape == (h, w, 4)
+    s.config["BLOOM"] = True
+    with pytest.raises(NotImplementedError):
+        s.render(w, h)
+    s.close()
+    if (Wd, w) == (64, 128):
+        g = golden("display_64_to_128")
+        s = make(pkg, 16, 16, 64, 64)
+        s.writeField("dye", g["in_dye"]); s.config["BACK_COLOR"] = {"r": 30, "g": 60, "b": 200}
+        assert bits_equal(s.render(128, 128), g["shaded"])
+        s.close()

@@ -96,3 +96,17 @@ def test_p4_report_distance_to_desktop_webgl(oracle, capsys):
             print(f"\n[P4] {name}: 1-step max-rel vs fp32 oracle: " +
                   ", ".join(f"{k}={v:.2e}" for k, v in e.items()))
         assert max(e.values()) < bound
+
+
+@pytest.mark.parametrize("name,exact", [("display_64_to_128", True), ("display_40x28_to_50x30", False)])
+def test_display_matches_executed_reference_shaders(oracle, name, exact):
+    """render() with bloom / sunrays off (first half) against the executed
+    colorShader + displayShaderSource + blend."""
+    g = golden(name); O = oracle
+    back = tuple(float(x) / 255 for x in g["back"])
+    for key, shading in (("shaded", True), ("flat", False)):
+        got = O.display(g["in_dye"], int(g["w"]), int(g["h"]), shading, back)
+        if exact:
+            assert bits_equal(got, g[key]), key
+        else:
+            assert max_rel(got, g[key]) < 1e-5, key

@@ -78,6 +78,8 @@ struct fluid {
     struct StepGraph { cudaGraphExec_t exec = nullptr; int flip_v = 0, flip_p = 0, flip_dye = 0, kernels = 0, jacobi_launches = 0; };
     std::map<std::string, StepGraph> graphs;
     uint64_t graph_launches = 0, graph_captures = 0;
+    float4* frame = nullptr;         // render target of fluid_render (w x h RGBA fp32), grown on demand
+    size_t frame_cells = 0;
     bool slab() const { return world > 1; }
     int lrows() const { return row1 - row0 + 2 * G; }
     int ldrows() const { return drow1 - drow0 + 2 * Gd; }
@@ -735,6 +737,7 @@ void fluid_destroy(fluid_t* h) {
     }
     free_fields(h);
     cudaFree(h->halo_flag);
+    cudaFree(h->frame);
     if (h->comm) { ncdl::api().CommDestroy(h->comm); h->comm = nullptr; }
     if (h->pin_a) cudaFreeHost(h->pin_a);
     if (h->pin_b) cudaFreeHost(h->pin_b);
@@ -1119,6 +1122,29 @@ int fluid_pressure_solve_host(fluid_t* h, const float* div_host, float* p_host, 
     CU(cudaMemcpyAsync((float*)h->pressure.read + go, p_host, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     int rc = run_jacobi(h, iters, true, nullptr); if (rc) return rc;
     CU(cudaMemcpyAsync(p_host, (float*)h->pressure.read + go, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return FLUID_OK;
+}
+
+// render(target) of S:1296-1317 for config.BLOOM = config.SUNRAYS = false, TRANSPARENT = false:
+// background colour, then the display shader (optionally SHADING) blended over it.
+int fluid_render(fluid_t* h, int width, int height, int shading, float back_r, float back_g,
+                 float back_b, float* host_rgba, size_t n_floats) {
+    if (!h || !host_rgba || width < 1 || height < 1) return fail(h, FLUID_ERR_INVALID, "bad argument");
+    if (h->slab()) return not_on_slab(h, "fluid_render");
+    const size_t cells = (size_t)width * height;
+    if (n_floats != 4 * cells) return fail(h, FLUID_ERR_INVALID, "render target has %zu floats, caller passed %zu", 4 * cells, n_floats);
+    if (cells > h->frame_cells) {
+        CU(cudaStreamSynchronize(h->stream));
+        cudaFree(h->frame); h->frame = nullptr; h->frame_cells = 0;
+        CU(cudaMalloc((void**)&h->frame, cells * sizeof(float4)));
+        h->frame_cells = cells;
+    }
+    dim3 b(32, 8);
+    display_kernel<<<grid2d(width, height, b), b, 0, h->stream>>>((const float4*)h->dye.read, h->cfg.dye_w, h->cfg.dye_h,
+                                                                h->frame, width, height, shading, back_r, back_g, back_b);
+    int rc = check_launch(h, "display_kernel"); if (rc) return rc;
+    CU(cudaMemcpyAsync(host_rgba, h->frame, cells * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return FLUID_OK;
 }

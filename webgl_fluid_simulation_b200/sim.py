@@ -38,9 +38,14 @@ def default_config() -> dict:
         "CURL": 30,
         "SPLAT_RADIUS": 0.25,
         "SPLAT_FORCE": 6000,
+        "SHADING": True,
         "COLORFUL": True,
         "COLOR_UPDATE_SPEED": 10,
         "PAUSED": False,
+        "BACK_COLOR": {"r": 0, "g": 0, "b": 0},
+        "TRANSPARENT": False,
+        "BLOOM": False,          # post-FX are not built (second half): render() refuses them
+        "SUNRAYS": False,
     }
 
 
@@ -319,6 +324,27 @@ class FluidSimulation:
     def writeField(self, name, array):
         a = np.ascontiguousarray(array, np.float32)
         self._check(self._L.fluid_write(self._h, FIELD[name], a.ctypes.data_as(C.c_void_p), a.size))
+
+    def render(self, width=None, height=None) -> np.ndarray:
+        """render(target), S:1296-1317, for BLOOM = SUNRAYS = TRANSPARENT = false: background colour
+        + shaded dye, (height, width, 4) float32 RGBA, row 0 = bottom.  Defaults to the canvas size
+        (target == null branch, S:1332-1333)."""
+        if self.config.get("BLOOM") or self.config.get("SUNRAYS") or self.config.get("TRANSPARENT"):
+            raise NotImplementedError("bloom / sunrays / transparent display are not built (DESIGN.md: out of scope this round)")
+        w = int(width or self.canvas["width"]); h = int(height or self.canvas["height"])
+        bc = self.config["BACK_COLOR"]                       # normalizeColor, S:1599-1606
+        out = np.empty((h, w, 4), np.float32)
+        self._check(self._L.fluid_render(self._h, w, h, 1 if self.config["SHADING"] else 0,
+                                         bc["r"] / 255, bc["g"] / 255, bc["b"] / 255,
+                                         out.ctypes.data_as(C.c_void_p), out.size))
+        return out
+
+    @staticmethod
+    def textureToCanvas(rgba: np.ndarray) -> np.ndarray:
+        """normalizeTexture + textureToCanvas (S:309-349): clamp01 * 255 truncated into a Uint8
+        image, flipped so that row 0 is the TOP (canvas order)."""
+        img = (np.clip(rgba, 0.0, 1.0) * 255.0).astype(np.uint8)
+        return img[::-1].copy()
 
     def sync(self):
         self._check(self._L.fluid_sync(self._h))
