@@ -189,8 +189,14 @@ def main():
     ap.add_argument("--jacobi-block", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--quick", action="store_true", help="timed region only (tuning runs): no e2e / naive / full-step / cpu legs")
+    ap.add_argument("--grid", type=int, default=4096, help="square grid size of the workload (BASELINE configs: 4096 / 8192 / 16384)")
+    ap.add_argument("--iters", type=int, default=50, help="Jacobi iterations per solve (BASELINE configs: 50 / 40 / 80)")
+    ap.add_argument("--strong", action="store_true", help="N>1: split ONE grid x grid domain into N row slabs (default: weak, one grid x grid slab per GPU)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    global W, H, ITERS
+    W = H = args.grid
+    ITERS = args.iters
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -209,8 +215,10 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    p0, d0 = synth_inputs()
     cfg = {"SIM_RESOLUTION": W, "DYE_RESOLUTION": 64, "PRESSURE_ITERATIONS": ITERS}
+    if world > 1 and args.strong:
+        H = args.grid // world                           # rows per rank of the ONE grid x grid domain
+    p0, d0 = synth_inputs()
     if world == 1:
         sim = pkg.FluidSimulation(cfg, 1024, 1024, device=local, jacobi_block=args.jacobi_block)
     else:
@@ -284,11 +292,12 @@ def main():
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"pressure solve {W}x{W} fp32, {ITERS} Jacobi iterations (BASELINE configs[2])",
+        "scaling": "strong" if (args.strong and world > 1) else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"pressure solve {W}x{W} fp32, {ITERS} Jacobi iterations" + (" (BASELINE configs[2])" if (W, ITERS) == (4096, 50) else ""),
                    "l2": "working set 192 MiB (p x2 + div) > 126 MB L2; no explicit flush",
                    "parallelism": "single GPU" if world == 1 else
-                   f"{world} row slabs of {W}x{H} (global grid {W}x{H * world}), NCCL halo exchange of p/div rows per blocked launch"},
+                   f"{world} row slabs of {W}x{H} (global grid {W}x{H * world}); one deep halo exchange per solve "
+                   f"({ITERS + 1} rows of p + {ITERS} of div per neighbour), transport " + os.environ.get("FLUID_HALO", "p2p")},
         "clocks": clk.summary(), "gpu_launches": gpu_launches, "roofline": roofline,
         "host_enqueue_ms_per_step": HOST_MS.get("solve"),
     }
