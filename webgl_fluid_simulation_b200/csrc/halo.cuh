@@ -1,0 +1,179 @@
+// halo.cuh — slab halo exchange: the peer-memory transport (IPC-mapped arenas, one push kernel with
+// the free/ready handshake) and the NCCL send/recv fallback.  Included by fluid.cu inside its
+// anonymous namespace, after `struct fluid`, fail(), CU() and check_launch() are defined.
+#pragma once
+
+// ---- halo exchange (NCCL point-to-point; all buffers and both neighbours in ONE group) ------------
+// For each item: sends my top `n` owned rows up and my bottom `n` owned rows down, receives the
+// neighbours' rows into my ghost rows.  `base` is local row 0 of a buffer whose local row 0 is
+// global row `off`.  Halo messages are latency-bound (a 4096-float row is 16 KiB), so everything
+// that can travel together does.
+// `which` names the buffer for the peer-memory path: 0 velocity.read, 1 pressure.read, 2 dye.read,
+// 3 divergence (the neighbour's copy of the same buffer is found through its exported offsets and
+// the SPMD-identical swap parity).
+enum { HB_VELOCITY = 0, HB_PRESSURE = 1, HB_DYE = 2, HB_DIVERGENCE = 3 };
+struct HaloItem { void* base; size_t row_bytes; int off, r0, r1, n; int which; };
+
+struct PushSeg { const float4* src; float4* dst; unsigned long long n4; };
+struct PushArgs {
+    PushSeg seg[8];
+    int count;
+    unsigned seq;
+    unsigned* my_flags;        // [0] ready-from-below [1] ready-from-above [2] free-from-below [3] free-from-above
+    unsigned* peer_flags[2];   // the same four words in the neighbours' arenas (IPC-mapped); [0] below, [1] above
+    int present[2];
+    unsigned* counter;         // block-completion counter (local)
+    int* err;                  // set when a bounded spin times out (reported as FLUID_ERR_HALO)
+    unsigned long long* dbg;   // FLUID_DEBUG_HALO_TIMING: [0] sum wait-free ns [1] sum push ns [2] sum wait-ready ns [3] count [4] t_start
+};
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t;
+}
+// bounded spin: a neighbour that never arrives costs 4 s and an error flag, never a hung GPU
+__device__ __forceinline__ void spin_until(const unsigned* flag, unsigned seq, int* err) {
+    const unsigned long long t0 = global_ns();
+    while ((int)(ld_acquire_sys(flag) - seq) < 0) {
+        if (global_ns() - t0 > 4000000000ull) { *err = 2; break; }
+        __nanosleep(100);
+    }
+}
+
+// The whole producer side of one halo exchange in ONE kernel:
+//   (a) tell the neighbours my ghost rows may be overwritten (this kernel is stream-ordered after
+//       every kernel of mine that read them), (b) wait until theirs are free, (c) store my boundary
+//       rows straight into their ghost rows — dst pointers are the neighbours' arenas mapped through
+//       CUDA IPC, so the stores travel over NVLink / NVSwitch — and (d) once the last block is
+//       done, release-store "ready = seq" into the neighbours' flag words.
+__global__ void __launch_bounds__(256) halo_push_kernel(PushArgs a) {
+    if (threadIdx.x == 0) {
+        unsigned long long t0 = 0;
+        if (blockIdx.x == 0) {
+            if (a.dbg) { t0 = global_ns(); a.dbg[4] = t0; }
+            for (int side = 0; side < 2; ++side)
+                if (a.present[side]) st_release_sys(a.peer_flags[side] + (side == 0 ? 3 : 2), a.seq);
+        }
+        for (int side = 0; side < 2; ++side)
+            if (a.present[side]) spin_until(a.my_flags + (side == 0 ? 2 : 3), a.seq, a.err);
+        if (blockIdx.x == 0 && a.dbg) atomicAdd(a.dbg + 0, global_ns() - t0);
+    }
+    __syncthreads();
+    for (int k = 0; k < a.count; ++k) {
+        const float4* __restrict__ s = a.seg[k].src;
+        float4* __restrict__ d = a.seg[k].dst;
+        const unsigned long long n4 = a.seg[k].n4;
+        for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+             i += (unsigned long long)gridDim.x * blockDim.x)
+            d[i] = s[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned done = atomicAdd(a.counter, 1u);
+        if (done == gridDim.x - 1) {
+            *a.counter = 0;
+            __threadfence_system();
+            for (int side = 0; side < 2; ++side)
+                if (a.present[side]) st_release_sys(a.peer_flags[side] + (side == 0 ? 1 : 0), a.seq);
+            if (a.dbg) { atomicAdd(a.dbg + 1, global_ns() - a.dbg[4]); atomicAdd(a.dbg + 3, 1ull); }
+        }
+    }
+}
+
+// (e) consumer side: one thread acquires the neighbours' "ready" words; kernels after it in the
+// stream then read the ghost rows the neighbours stored.
+__global__ void halo_wait_kernel(const unsigned* my_flags, int present_below, int present_above,
+                                 unsigned seq, int* err, unsigned long long* dbg) {
+    const unsigned long long t0 = dbg ? global_ns() : 0;
+    if (present_below) spin_until(my_flags + 0, seq, err);
+    if (present_above) spin_until(my_flags + 1, seq, err);
+    if (dbg) atomicAdd(dbg + 2, global_ns() - t0);
+}
+
+int exchange_p2p(fluid_t* h, const HaloItem* it, int count) {
+    PushArgs pa{};
+    pa.seq = ++h->p2p_seq;
+    pa.my_flags = (unsigned*)(h->arena + h->off_flags);
+    pa.counter = pa.my_flags + 8;
+    pa.err = h->halo_flag;
+    static const bool dbg = getenv("FLUID_DEBUG_HALO_TIMING") != nullptr;
+    pa.dbg = dbg ? (unsigned long long*)(h->arena + h->off_flags + 128) : nullptr;
+    unsigned long long total4 = 0;
+    for (int side = 0; side < 2; ++side) {
+        pa.present[side] = h->peer[side].present ? 1 : 0;
+        pa.peer_flags[side] = h->peer[side].present ? (unsigned*)(h->peer[side].base + h->peer[side].off_flags) : nullptr;
+    }
+    for (int k = 0; k < count; ++k) {
+        const HaloItem& q = it[k];
+        if (q.n <= 0) continue;
+        for (int side = 0; side < 2; ++side) {
+            const fluid::Peer& P = h->peer[side];
+            if (!P.present) continue;
+            size_t poff; int proff;
+            switch (q.which) {
+                case HB_VELOCITY: poff = P.off_v[h->par_v]; proff = P.roff; break;
+                case HB_PRESSURE: poff = P.off_p[h->par_p]; proff = P.roff; break;
+                case HB_DYE: poff = P.off_dye[h->par_dye]; proff = P.droff; break;
+                default: poff = P.off_div; proff = P.roff; break;
+            }
+            const int g0 = (side == 1) ? q.r1 - q.n : q.r0;          // my owned rows that the neighbour needs
+            const char* src = (const char*)q.base + (size_t)(g0 - q.off) * q.row_bytes;
+            char* dst = P.base + poff + (size_t)(g0 - proff) * q.row_bytes;
+            if (pa.count >= 8) return fail(h, FLUID_ERR_INVALID, "too many halo segments");
+            PushSeg& sg = pa.seg[pa.count++];
+            sg.src = (const float4*)src; sg.dst = (float4*)dst; sg.n4 = (unsigned long long)q.n * q.row_bytes / 16;
+            total4 = std::max(total4, sg.n4);
+        }
+    }
+    const unsigned blocks = (unsigned)std::min<unsigned long long>(std::max<unsigned long long>((total4 + 255) / 256, 1), (unsigned long long)h->sm_count * 2);
+    halo_push_kernel<<<blocks, 256, 0, h->stream>>>(pa);
+    int rc = check_launch(h, "halo_push_kernel"); if (rc) return rc;
+    halo_wait_kernel<<<1, 1, 0, h->stream>>>(pa.my_flags, pa.present[0], pa.present[1], pa.seq, pa.err, pa.dbg);
+    rc = check_launch(h, "halo_wait_kernel"); if (rc) return rc;
+    ++h->halo_groups;
+    return FLUID_OK;
+}
+
+int exchange_many(fluid_t* h, const HaloItem* it, int count) {
+    if (!h->slab()) return FLUID_OK;
+    for (int k = 0; k < count; ++k)
+        if (it[k].n > it[k].r1 - it[k].r0)
+            return fail(h, FLUID_ERR_HALO, "halo of %d rows exceeds the slab height %d (use fewer GPUs or a taller grid)",
+                        it[k].n, it[k].r1 - it[k].r0);
+    static const bool skip = getenv("FLUID_DEBUG_SKIP_HALO") != nullptr;   // TIMING EXPERIMENTS ONLY: wrong results
+    if (skip) return FLUID_OK;
+    if (h->p2p) return exchange_p2p(h, it, count);
+    ncdl::Api& N = ncdl::api();
+    int rc = N.GroupStart();
+    for (int k = 0; k < count && !rc; ++k) {
+        const HaloItem& q = it[k];
+        if (q.n <= 0) continue;
+        char* b = static_cast<char*>(q.base);
+        auto at = [&](int grow) { return b + (size_t)(grow - q.off) * q.row_bytes; };
+        const size_t bytes = (size_t)q.n * q.row_bytes;
+        if (h->rank + 1 < h->world) {
+            if (!rc) rc = N.Send(at(q.r1 - q.n), bytes, ncdl::ncclInt8, h->rank + 1, h->comm, h->stream);
+            if (!rc) rc = N.Recv(at(q.r1), bytes, ncdl::ncclInt8, h->rank + 1, h->comm, h->stream);
+        }
+        if (h->rank > 0) {
+            if (!rc) rc = N.Send(at(q.r0), bytes, ncdl::ncclInt8, h->rank - 1, h->comm, h->stream);
+            if (!rc) rc = N.Recv(at(q.r0 - q.n), bytes, ncdl::ncclInt8, h->rank - 1, h->comm, h->stream);
+        }
+    }
+    const int rc2 = N.GroupEnd();
+    if (rc || rc2) return fail(h, FLUID_ERR_NCCL, "NCCL halo exchange failed: %s", N.GetErrorString(rc ? rc : rc2));
+    ++h->halo_groups;
+    return FLUID_OK;
+}
+
+int exchange_rows(fluid_t* h, int which, void* base, size_t row_bytes, int off, int r0, int r1, int n) {
+    HaloItem it{base, row_bytes, off, r0, r1, n, which};
+    return exchange_many(h, &it, 1);
+}
+
