@@ -275,6 +275,7 @@ def main():
         "algorithmic_bytes_per_update": ALGO_BYTES_PER_UPDATE, "blocked_launches_per_step": per_step_launches,
         "avg_launch_ms": ms / (args.steps * per_step_launches),
         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_UPDATE * W * H * ITERS / per_step_launches,
+        "updates_per_launch": W * H * ITERS / per_step_launches,
         "compulsory_frac": (ALGO_BYTES_PER_UPDATE * W * H * per_step_launches * args.steps / (ms * 1e-3) / 1e9) / peak,
         "note": "temporal blocking runs several sweeps per launch out of registers, so the "
                 "12 B/update algorithmic figure exceeds what DRAM actually moves; frac > 1 is "

@@ -14,7 +14,7 @@ rng = np.random.default_rng(0)
 p = rng.standard_normal((W, W)).astype(np.float32)
 d = rng.uniform(-1, 1, (W, W)).astype(np.float32)
 print(f"# {W}x{W}, {ITERS} iterations; ms per solve, G updates/s")
-for kb in (1, 2, 4, 5, 6, 7, 8, 9, 10):
+for kb in (1, 2, 4, 6, 8, 9, 10, 11, 12):
     for rows in ((0,) if kb == 1 else (0, 32, 48, 64, 96, 128, 192, 256, 512)):
         os.environ["FLUID_JACOBI_ROWS"] = str(rows)
         flags = pkg.FLAG_NAIVE_JACOBI if kb == 1 else 0
