@@ -298,7 +298,7 @@ def main():
                    "l2": "working set 192 MiB (p x2 + div) > 126 MB L2; no explicit flush",
                    "parallelism": "single GPU" if world == 1 else
                    f"{world} row slabs of {W}x{H} (global grid {W}x{H * world}); one deep halo exchange per solve "
-                   f"({ITERS + 1} rows of p + {ITERS} of div per neighbour), transport " + os.environ.get("FLUID_HALO", "p2p")},
+                   f"({ITERS + 1} rows of p + {ITERS} of div per neighbour), transport " + getattr(sim, "halo_transport", "-")},
         "clocks": clk.summary(), "gpu_launches": gpu_launches, "roofline": roofline,
         "host_enqueue_ms_per_step": HOST_MS.get("solve"),
     }

@@ -127,6 +127,7 @@ int fluid_nccl_unique_id(void* out_uid, size_t uid_bytes); /* uid_bytes must be 
  * without it the NCCL send/recv path is used. */
 int fluid_p2p_export(fluid_t* h, void* blob, size_t blob_bytes);   /* blob_bytes >= 256 */
 int fluid_p2p_connect(fluid_t* h, const void* blob_below, const void* blob_above);
+int fluid_p2p_disable(fluid_t* h);   /* back to NCCL; call on every rank if any rank failed to connect */
 
 void fluid_destroy(fluid_t* h);
 

@@ -16,7 +16,7 @@ CSRC = os.path.join(_HERE, "csrc")
 # every symbol include/fluid.h declares (tests check the .so exports exactly these)
 SYMBOLS = [
     "fluid_abi_version", "fluid_config_default", "fluid_get_resolution", "fluid_create",
-    "fluid_create_slab", "fluid_nccl_unique_id", "fluid_p2p_export", "fluid_p2p_connect", "fluid_destroy", "fluid_resize", "fluid_step",
+    "fluid_create_slab", "fluid_nccl_unique_id", "fluid_p2p_export", "fluid_p2p_connect", "fluid_p2p_disable", "fluid_destroy", "fluid_resize", "fluid_step",
     "fluid_splat", "fluid_set_param", "fluid_get_param", "fluid_pass_curl", "fluid_pass_vorticity",
     "fluid_pass_divergence", "fluid_pass_clear_pressure", "fluid_pass_jacobi",
     "fluid_pass_pressure_solve", "fluid_pass_gradient_subtract", "fluid_pass_advect_velocity",
@@ -87,6 +87,7 @@ def lib():
     L.fluid_nccl_unique_id.argtypes = [vp, sz]
     L.fluid_p2p_export.argtypes = [vp, vp, sz]
     L.fluid_p2p_connect.argtypes = [vp, vp, vp]
+    L.fluid_p2p_disable.argtypes = [vp]
     L.fluid_destroy.argtypes = [vp]; L.fluid_destroy.restype = None
     L.fluid_resize.argtypes = [vp, i, i, i, i]
     L.fluid_step.argtypes = [vp, f]

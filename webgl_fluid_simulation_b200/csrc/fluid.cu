@@ -549,6 +549,16 @@ int fluid_p2p_connect(fluid_t* h, const void* blob_below, const void* blob_above
     return FLUID_OK;
 }
 
+// Back to the NCCL transport (used by launchers when ANY rank failed to map its neighbours, so
+// that all ranks keep using the same one).
+int fluid_p2p_disable(fluid_t* h) {
+    if (!h) return FLUID_ERR_INVALID;
+    if (h->stream) CU(cudaStreamSynchronize(h->stream));
+    for (auto& p : h->peer) if (p.present && p.base) { cudaIpcCloseMemHandle(p.base); p.base = nullptr; p.present = false; }
+    h->p2p = false;
+    return FLUID_OK;
+}
+
 void fluid_destroy(fluid_t* h) {
     if (!h) return;
     cudaSetDevice(h->device);
