@@ -114,6 +114,7 @@ def cpu_port_rate(budget_s=12.0):
     import ctypes as C
     from oracle import oracle as O
     L = O.lib()
+    O.use_all_cores()
     p, d = synth_inputs()
     tmp = np.empty_like(p)
     fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
@@ -138,6 +139,7 @@ def run_reference(args, rank, world):
     import ctypes as C
     from oracle import oracle as O
     L = O.lib()
+    O.use_all_cores()                                    # torchrun exports OMP_NUM_THREADS=1
     p, d = synth_inputs()
     tmp = np.empty_like(p)
     fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))

@@ -20,6 +20,16 @@
 
 static inline int clampi(int a, int lo, int hi) { return a < lo ? lo : (a > hi ? hi : a); }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU-baseline legs of bench.py widen the
+ * team again to the cores the process may actually use. */
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int oracle_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

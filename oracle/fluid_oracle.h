@@ -69,6 +69,7 @@ void oracle_sim_step(oracle_sim* s, float dt);                      /* S:1231-12
 void oracle_sim_splat(oracle_sim* s, float x, float y, float dx, float dy, float r, float g,
                       float b);                                    /* S:1441-1462 */
 int oracle_num_threads(void);
+void oracle_set_num_threads(int n);
 
 #ifdef __cplusplus
 }

@@ -71,6 +71,18 @@ def num_threads() -> int:
     return int(lib().oracle_num_threads())
 
 
+def use_all_cores() -> int:
+    """Size the OpenMP team to the cores this process may run on (torchrun sets OMP_NUM_THREADS=1)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    L = lib()
+    L.oracle_set_num_threads.argtypes = [C.c_int]; L.oracle_set_num_threads.restype = None
+    L.oracle_set_num_threads(int(n))
+    return num_threads()
+
+
 # Array conventions: scalar fields are (H, W); velocity (H, W, 2); dye (Hd, Wd, 4); row 0 = bottom.
 
 def curl(v):
