@@ -43,3 +43,11 @@ def oracle():
     from oracle import oracle as O
     O.build()
     return O
+
+
+def free_port() -> int:
+    """A TCP port nobody is listening on right now (rendezvous of the multi-process tests)."""
+    import socket
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as sk:
+        sk.bind(("127.0.0.1", 0))
+        return sk.getsockname()[1]

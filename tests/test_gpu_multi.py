@@ -5,6 +5,8 @@ import sys
 
 import pytest
 
+from conftest import free_port
+
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -22,7 +24,7 @@ def test_slabs_equal_single_gpu_bitwise(world, halo):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-           "--master-addr", "127.0.0.1", "--master-port", str(29700 + world + (10 if halo == "nccl" else 0)), os.path.join(ROOT, "tools", "slab_check.py")]
+           "--master-addr", "127.0.0.1", "--master-port", str(free_port()), os.path.join(ROOT, "tools", "slab_check.py")]
     env = dict(os.environ, FLUID_HALO=halo, SLAB_ITERS="50", SLAB_H="1024", SLAB_HD="2048")
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert "SLAB_CHECK ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

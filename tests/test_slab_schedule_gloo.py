@@ -106,7 +106,8 @@ def test_slab_schedule_is_exact(world, plan_iters):
     plan_iters = 5: ghost zone too thin for 23 sweeps -> per-launch fallback."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29650 + world + plan_iters
+    from conftest import free_port
+    port = free_port()
     procs = [ctx.Process(target=_worker, args=(r, world, port, q, plan_iters)) for r in range(world)]
     for pr in procs:
         pr.start()
