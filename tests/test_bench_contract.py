@@ -18,7 +18,8 @@ def test_reference_arm_prints_the_contract_line():
     for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
               "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
         assert k in d, k
-    assert d["impl"] == "reference" and d["metric"] == "jacobi_cell_updates_per_sec" and d["unit"] == "updates/s"
+    want = json.load(open(os.path.join(ROOT, "BASELINE.json")))["metric"]
+    assert d["impl"] == "reference" and d["metric"] == want and d["unit"] == "cell-updates/s"
     assert d["value"] > 0 and d["higher_is_better"] is True and d["vs_baseline"] is None and d["dtype"] == "f32"
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["gpu_launches"] == 0
