@@ -305,7 +305,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "strong" if (args.strong and world > 1) else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"pressure solve {W}x{W} fp32, {ITERS} Jacobi iterations" + (" (BASELINE configs[2])" if (W, ITERS) == (4096, 50) else ""),
-                   "l2": "working set 192 MiB (p x2 + div) > 126 MB L2; no explicit flush",
+                   "l2": f"working set {12 * W * H / 2**20:.0f} MiB per GPU (p x2 + div) vs 126 MB L2; no explicit flush between steps",
                    "parallelism": "single GPU" if world == 1 else
                    f"{world} row slabs of {W}x{H} (global grid {W}x{H * world}); one deep halo exchange per solve "
                    f"({ITERS + 1} rows of p + {ITERS} of div per neighbour), transport " + getattr(sim, "halo_transport", "-")},
