@@ -307,6 +307,178 @@ void oracle_display(const float* dye, int Wd, int Hd, float* out, int w, int h, 
     }
 }
 
+/* ---- post-FX (bloom, sunrays) and the full display: SURVEY section 8f rank 1, second half --------------------
+ * ORACLE SIDE ONLY so far: the CUDA kernels for these passes are not built yet. */
+
+/* LINEAR fetch with CLAMP_TO_EDGE or REPEAT wrap, C channels */
+static inline void linear_fetch_w(const float* tex, int W, int H, int C, float uvx, float uvy, int repeat, float* out) {
+    if (!repeat) { linear_fetch(tex, W, H, C, uvx, uvy, out); return; }
+    const float u = uvx * (float)W - 0.5f, v = uvy * (float)H - 0.5f;
+    const float fi = floorf(u), fj = floorf(v);
+    const float a = u - fi, b = v - fj;
+    long long i0 = (long long)fi % W, j0 = (long long)fj % H;
+    if (i0 < 0) i0 += W;
+    if (j0 < 0) j0 += H;
+    const long long i1 = (i0 + 1) % W, j1 = (j0 + 1) % H;
+    const float w00 = (1.0f - a) * (1.0f - b), w10 = a * (1.0f - b), w01 = (1.0f - a) * b, w11 = a * b;
+    const float* t00 = tex + ((size_t)j0 * W + i0) * C; const float* t10 = tex + ((size_t)j0 * W + i1) * C;
+    const float* t01 = tex + ((size_t)j1 * W + i0) * C; const float* t11 = tex + ((size_t)j1 * W + i1) * C;
+    for (int k = 0; k < C; ++k) out[k] = ((w00 * t00[k] + w10 * t10[k]) + w01 * t01[k]) + w11 * t11[k];
+}
+
+/* bloomPrefilterShader S:614-631, drawn into the bloom FBO (w x h) sampling dye.read */
+void oracle_bloom_prefilter(const float* dye, int Wd, int Hd, float* out, int w, int h, float curve0,
+                            float curve1, float curve2, float threshold) {
+#pragma omp parallel for schedule(static)
+    for (int j = 0; j < h; ++j) {
+        const float uvy = ((float)j + 0.5f) / (float)h;
+        for (int i = 0; i < w; ++i) {
+            const float uvx = ((float)i + 0.5f) / (float)w;
+            float c[4];
+            linear_fetch(dye, Wd, Hd, 4, uvx, uvy, c);
+            const float br = fmaxf(c[0], fmaxf(c[1], c[2]));
+            float rq = fminf(fmaxf(br - curve0, 0.0f), curve1);
+            rq = (curve2 * rq) * rq;
+            const float f = fmaxf(rq, br - threshold) / fmaxf(br, 0.0001f);
+            float* o = out + ((size_t)j * w + i) * 4;
+            o[0] = c[0] * f; o[1] = c[1] * f; o[2] = c[2] * f; o[3] = 0.0f;
+        }
+    }
+}
+
+/* bloomBlurShader S:633-651 / bloomFinalShader S:653-674: average of the 4 LINEAR taps one SOURCE
+ * texel left/right/up/down; `add`: blendFunc(ONE, ONE) onto dst (S:1374-1375); scale = intensity. */
+void oracle_box4(const float* src, int ws, int hs, float* dst, int w, int h, float scale, int add) {
+    const float tsx = (float)(1.0 / (double)ws), tsy = (float)(1.0 / (double)hs);
+#pragma omp parallel for schedule(static)
+    for (int j = 0; j < h; ++j) {
+        const float uvy = ((float)j + 0.5f) / (float)h;
+        for (int i = 0; i < w; ++i) {
+            const float uvx = ((float)i + 0.5f) / (float)w;
+            float L[4], R[4], T[4], B[4];
+            linear_fetch(src, ws, hs, 4, uvx - tsx, uvy, L);
+            linear_fetch(src, ws, hs, 4, uvx + tsx, uvy, R);
+            linear_fetch(src, ws, hs, 4, uvx, uvy + tsy, T);
+            linear_fetch(src, ws, hs, 4, uvx, uvy - tsy, B);
+            float* o = dst + ((size_t)j * w + i) * 4;
+            for (int k = 0; k < 4; ++k) {
+                float sum = (((0.0f + L[k]) + R[k]) + T[k]) + B[k];
+                sum = sum * 0.25f;
+                sum = sum * scale;
+                o[k] = add ? sum + o[k] : sum;
+            }
+        }
+    }
+}
+
+/* sunraysMaskShader S:676-691 into a dye-sized RGBA target */
+void oracle_sunrays_mask(const float* dye, float* mask, int Wd, int Hd) {
+#pragma omp parallel for schedule(static)
+    for (int j = 0; j < Hd; ++j) {
+        const float uvy = ((float)j + 0.5f) / (float)Hd;
+        for (int i = 0; i < Wd; ++i) {
+            const float uvx = ((float)i + 0.5f) / (float)Wd;
+            float c[4];
+            linear_fetch(dye, Wd, Hd, 4, uvx, uvy, c);
+            const float br = fmaxf(c[0], fmaxf(c[1], c[2]));
+            float* o = mask + ((size_t)j * Wd + i) * 4;
+            o[0] = c[0]; o[1] = c[1]; o[2] = c[2];
+            o[3] = 1.0f - fminf(fmaxf(br * 20.0f, 0.0f), 0.8f);
+        }
+    }
+}
+
+/* sunraysShader S:693-724: 16-step march towards the centre over the mask's alpha */
+void oracle_sunrays(const float* mask, int Wm, int Hm, float* out, int w, int h, float weight) {
+    const float Density = 0.3f, Decay = 0.95f, Exposure = 0.7f;
+    const float f = (float)(1.0 / 16.0) * Density;                 /* 1.0 / float(ITERATIONS) * Density */
+#pragma omp parallel for schedule(static)
+    for (int j = 0; j < h; ++j) {
+        const float uvy = ((float)j + 0.5f) / (float)h;
+        for (int i = 0; i < w; ++i) {
+            const float uvx = ((float)i + 0.5f) / (float)w;
+            float cx = uvx, cy = uvy;
+            float dx = uvx - 0.5f, dy = uvy - 0.5f;
+            dx = dx * f; dy = dy * f;
+            float illum = 1.0f, t[4];
+            linear_fetch(mask, Wm, Hm, 4, uvx, uvy, t);
+            float color = t[3];
+            for (int k = 0; k < 16; ++k) {
+                cx = cx - dx; cy = cy - dy;
+                linear_fetch(mask, Wm, Hm, 4, cx, cy, t);
+                color = color + (t[3] * illum) * weight;
+                illum = illum * Decay;
+            }
+            out[(size_t)j * w + i] = color * Exposure;
+        }
+    }
+}
+
+/* blurShader S:478-494 with blurVertexShader S:461-476 on a one-channel texture (sunrays) */
+void oracle_blur3(const float* src, float* dst, int w, int h, float tsx, float tsy) {
+    const float off = 1.33333333f;
+#pragma omp parallel for schedule(static)
+    for (int j = 0; j < h; ++j) {
+        const float uvy = ((float)j + 0.5f) / (float)h;
+        for (int i = 0; i < w; ++i) {
+            const float uvx = ((float)i + 0.5f) / (float)w;
+            float c, l, r;
+            linear_fetch(src, w, h, 1, uvx, uvy, &c);
+            linear_fetch(src, w, h, 1, uvx - tsx * off, uvy - tsy * off, &l);
+            linear_fetch(src, w, h, 1, uvx + tsx * off, uvy + tsy * off, &r);
+            float sum = c * 0.29411764f;
+            sum = sum + l * 0.35294117f;
+            sum = sum + r * 0.35294117f;
+            dst[(size_t)j * w + i] = sum;
+        }
+    }
+}
+
+/* displayShaderSource S:549-612 with SHADING + BLOOM + SUNRAYS, over drawColor, premultiplied blend */
+void oracle_display_full(const float* dye, int Wd, int Hd, const float* bloom, int bw, int bh,
+                         const float* sun, int sw, int sh, const float* dither, int dw, int dh,
+                         float* out, int w, int h, const float* back_rgb) {
+    const float tsx = (float)(1.0 / (double)w), tsy = (float)(1.0 / (double)h);
+    const float dsx = (float)((double)w / (double)dw), dsy = (float)((double)h / (double)dh);   /* S:1626-1631 */
+#pragma omp parallel for schedule(static)
+    for (int j = 0; j < h; ++j) {
+        const float uvy = ((float)j + 0.5f) / (float)h;
+        for (int i = 0; i < w; ++i) {
+            const float uvx = ((float)i + 0.5f) / (float)w;
+            float c[4], lc[4], rc[4], tc[4], bc[4], bl[4], s, dn[3];
+            linear_fetch(dye, Wd, Hd, 4, uvx, uvy, c);
+            linear_fetch(dye, Wd, Hd, 4, uvx - tsx, uvy, lc);
+            linear_fetch(dye, Wd, Hd, 4, uvx + tsx, uvy, rc);
+            linear_fetch(dye, Wd, Hd, 4, uvx, uvy + tsy, tc);
+            linear_fetch(dye, Wd, Hd, 4, uvx, uvy - tsy, bc);
+            const float dx = LEN3(rc) - LEN3(lc), dy = LEN3(tc) - LEN3(bc);
+            const float nz = sqrtf(tsx * tsx + tsy * tsy);
+            const float nl = sqrtf((dx * dx + dy * dy) + nz * nz);
+            const float d = ((dx / nl) * 0.0f + (dy / nl) * 0.0f) + (nz / nl) * 1.0f;
+            const float diffuse = fminf(fmaxf(d + 0.7f, 0.7f), 1.0f);
+            linear_fetch(bloom, bw, bh, 4, uvx, uvy, bl);
+            linear_fetch(sun, sw, sh, 1, uvx, uvy, &s);
+            linear_fetch_w(dither, dw, dh, 3, uvx * dsx, uvy * dsy, 1, dn);
+            float noise = dn[0] * 2.0f - 1.0f;
+            float a = 0.0f;
+            float cc[3];
+            for (int k = 0; k < 3; ++k) {
+                float ck = (c[k] * diffuse) * s;
+                float bk = bl[k] * s;
+                bk = bk + noise / 255.0f;
+                bk = fmaxf(bk, 0.0f);
+                bk = fmaxf(1.055f * powf(bk, 0.416666667f) - 0.055f, 0.0f);       /* linearToGamma S:565-568 */
+                cc[k] = ck + bk;
+            }
+            a = fmaxf(cc[0], fmaxf(cc[1], cc[2]));
+            const float k1 = 1.0f - a;
+            float* o = out + ((size_t)j * w + i) * 4;
+            o[0] = cc[0] + back_rgb[0] * k1; o[1] = cc[1] + back_rgb[1] * k1; o[2] = cc[2] + back_rgb[2] * k1;
+            o[3] = a + 1.0f * k1;
+        }
+    }
+}
+
 void oracle_round_half(float* a, size_t n) {
 #pragma omp parallel for schedule(static)
     for (long long k = 0; k < (long long)n; ++k) a[k] = (float)(_Float16)a[k];

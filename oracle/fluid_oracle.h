@@ -51,6 +51,18 @@ void oracle_resample(const float* src, int Ws, int Hs, float* dst, int Wd, int H
 void oracle_display(const float* dye, int Wd, int Hd, float* out, int w, int h, int shading,
                     const float* back_rgb);
 
+/* post-FX chain (oracle side only so far): bloom S:614-674 + S:1350-1394, sunrays S:676-724 +
+ * S:1396-1419, full display S:549-612 */
+void oracle_bloom_prefilter(const float* dye, int Wd, int Hd, float* out, int w, int h, float curve0,
+                            float curve1, float curve2, float threshold);
+void oracle_box4(const float* src, int ws, int hs, float* dst, int w, int h, float scale, int add);
+void oracle_sunrays_mask(const float* dye, float* mask, int Wd, int Hd);
+void oracle_sunrays(const float* mask, int Wm, int Hm, float* out, int w, int h, float weight);
+void oracle_blur3(const float* src, float* dst, int w, int h, float tsx, float tsy);
+void oracle_display_full(const float* dye, int Wd, int Hd, const float* bloom, int bw, int bh,
+                         const float* sun, int sw, int sh, const float* dither, int dw, int dh,
+                         float* out, int w, int h, const float* back_rgb);
+
 /* fp16 storage emulation (S:138-147, S:986-1006): round every element through IEEE half, RNE */
 void oracle_round_half(float* a, size_t n);
 

@@ -151,6 +151,11 @@ def g_pow(x, y):
     return np.power(x, y).astype(F)
 
 
+def g_mod(x, y):                                                    # GLSL: x - y * floor(x / y)
+    if isinstance(x, V): return V(x.arr - x._co(y) * np.floor(x.arr / x._co(y)))
+    x = np.asarray(x, F); return (x - y * np.floor(x / y)).astype(F)
+
+
 def g_where(c, a, b):
     if isinstance(a, V) or isinstance(b, V):
         aa = a.arr if isinstance(a, V) else a
@@ -172,8 +177,9 @@ class Texture:
     """createFBO (S:1045-1077): w x h texels, `ch` stored channels (R / RG / RGBA), filter NEAREST
     or LINEAR, CLAMP_TO_EDGE, cleared to clearColor (0,0,0,1) (S:136, S:1059)."""
 
-    def __init__(self, w, h, ch, linear, half=False):
+    def __init__(self, w, h, ch, linear, half=False, repeat=False):
         self.w, self.h, self.ch, self.linear, self.half = w, h, ch, linear, half
+        self.repeat = repeat                # TEXTURE_WRAP REPEAT (the dithering texture, S:1133-1134)
         self.data = np.zeros((h, w, 4), F)
         self.data[..., 3] = 1.0
         self.texelSizeX = 1.0 / w          # JS doubles (S:1061-1062); narrowed by gl.uniform2f
@@ -189,8 +195,11 @@ class Texture:
         self.data = d
 
     def _fetch(self, ix, iy):
-        ix = np.clip(ix, 0, self.w - 1).astype(np.int64)
-        iy = np.clip(iy, 0, self.h - 1).astype(np.int64)
+        if self.repeat:
+            ix = np.mod(ix, self.w).astype(np.int64); iy = np.mod(iy, self.h).astype(np.int64)
+        else:
+            ix = np.clip(ix, 0, self.w - 1).astype(np.int64)
+            iy = np.clip(iy, 0, self.h - 1).astype(np.int64)
         return self.data[iy, ix]
 
     def sample(self, uv):
@@ -240,9 +249,14 @@ def extract_shader(js: str, name: str):
 
 
 def _preprocess(src: str, defines):
-    out, stack = [], [True]
+    out, stack, macros = [], [True], {}
     for line in src.splitlines():
         s = line.strip()
+        if s.startswith("#define"):
+            parts = s.split(None, 2)
+            if len(parts) == 3 and all(stack):
+                macros[parts[1]] = parts[2]
+            continue
         if s.startswith("#ifdef"):
             stack.append(s.split()[1] in defines)
         elif s.startswith("#else"):
@@ -250,14 +264,17 @@ def _preprocess(src: str, defines):
         elif s.startswith("#endif"):
             stack.pop()
         elif all(stack):
-            out.append(re.sub(r"//.*", "", line))
+            line = re.sub(r"//.*", "", line)
+            for k, v in macros.items():
+                line = re.sub(r"\b" + re.escape(k) + r"\b", v, line)
+            out.append(line)
     return "\n".join(out)
 
 
 _TYPES = r"(?:float|vec2|vec3|vec4|int|bool)"
 _RENAME = {"texture2D": "g_texture2D", "mix": "g_mix", "dot": "g_dot", "length": "g_length",
            "min": "g_min", "max": "g_max", "floor": "g_floor", "fract": "g_fract", "exp": "g_exp",
-           "abs": "g_abs", "normalize": "g_normalize", "clamp": "g_clamp", "pow": "g_pow"}
+           "abs": "g_abs", "normalize": "g_normalize", "clamp": "g_clamp", "pow": "g_pow", "mod": "g_mod"}
 
 
 def _expr(e: str) -> str:
@@ -292,6 +309,13 @@ def _stmts(body: str, ind: str):
                 m = re.match(r"([\w.]+)\s*=\s*(.*)$", st, re.S)
                 assert m, "only plain assignments are supported under if: " + st
                 py.append(f"{ind}{m.group(1)} = g_where({cond}, {_expr(m.group(2))}, {m.group(1)})")
+            i = b1 + 1
+            continue
+        mf = re.match(r"for\s*\(\s*int\s+(\w+)\s*=\s*(\w+)\s*;\s*\1\s*<\s*(\w+)\s*;\s*\1\+\+\s*\)", body[i:])
+        if mf:                                    # for (int i = A; i < B; i++) { ... }
+            b0 = body.index("{", i + mf.end() - 1); b1 = _match(body, b0, "{", "}")
+            py.append(f"{ind}for {mf.group(1)} in range({mf.group(2)}, {mf.group(3)}):")
+            py += _stmts(body[b0 + 1:b1], ind + "    ") or [ind + "    pass"]
             i = b1 + 1
             continue
         j = body.index(";", i)
@@ -358,7 +382,7 @@ class Program:
                 "g_mix": g_mix, "g_dot": g_dot, "g_length": g_length, "g_min": g_min,
                 "g_max": g_max, "g_floor": _map(_floor), "g_fract": _map(_fract),
                 "g_exp": _map(np.exp), "g_abs": _map(np.abs), "g_where": g_where, "g_copy": g_copy,
-                "g_normalize": g_normalize, "g_clamp": g_clamp, "g_pow": g_pow}
+                "g_normalize": g_normalize, "g_clamp": g_clamp, "g_pow": g_pow, "g_mod": g_mod}
         self.vs_env = dict(base); exec(self.vs_src, self.vs_env)
         self.fs_env = dict(base); exec(self.fs_src, self.fs_env)
         self.u = {}
@@ -371,7 +395,9 @@ class Program:
                 val = F(val)                         # gl.uniform1f
             self.u[k] = val
 
-    def blit(self, target: Texture):
+    def blit(self, target: Texture, blend=None):
+        """blend: None (gl.disable(BLEND)), "add" (blendFunc(ONE, ONE)) or "premult"
+        (blendFunc(ONE, ONE_MINUS_SRC_ALPHA))."""
         w, h = target.w, target.h
         # fragment centres in NDC: the quad spans [-1,1]^2 over the w x h viewport (S:917, S:931)
         xs = (np.arange(w, dtype=F) + F(0.5)) / F(w) * F(2.0) - F(1.0)
@@ -385,7 +411,15 @@ class Program:
         for k, val in self.u.items():               # helper functions (bilerp) read uniforms as globals
             self.fs_env[k] = val
         self.fs_env["main"](E)
-        target.store(E.gl_FragColor)
+        src = E.gl_FragColor
+        if blend is not None:
+            dst = target.data
+            full = np.broadcast_to(src.arr, dst.shape).astype(F)
+            if blend == "add":
+                src = V(full + dst)
+            elif blend == "premult":
+                src = V(full + dst * (F(1.0) - full[..., 3:4]))
+        target.store(src)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -519,6 +553,74 @@ class GLSLSim:
         src = target.data
         one_minus_a = (F(1.0) - src[..., 3:4]).astype(F)
         return (src + dst * one_minus_a).astype(F)                                          # S:1305
+
+    def render_postfx(self, width, height, dither, cfg=None, back_color=(0, 0, 0)):
+        """render(null) with BLOOM, SUNRAYS and SHADING on (the reference's desktop defaults,
+        S:70-84): applyBloom (S:1350-1394), applySunrays + blur (S:1396-1419), drawColor,
+        drawDisplay (S:1296-1348).  FBO sizes follow initBloomFramebuffers / initSunraysFramebuffers
+        (S:1012-1043) for a width x height drawing buffer.  `dither` is the 64x64 LDR_LLL1_0.png
+        as float RGB in [0,1].  Returns the target and the intermediate bloom / sunrays textures."""
+        js = open(REFERENCE_JS).read()
+        c = dict(BLOOM_ITERATIONS=8, BLOOM_RESOLUTION=256, BLOOM_INTENSITY=0.8, BLOOM_THRESHOLD=0.6,
+                 BLOOM_SOFT_KNEE=0.7, SUNRAYS_RESOLUTION=196, SUNRAYS_WEIGHT=1.0)
+        c.update(cfg or {})
+
+        def get_resolution(res):                                                    # S:1612-1624
+            ar = width / height
+            if ar < 1: ar = 1.0 / ar
+            mn, mx = int(np.floor(res + 0.5)), int(np.floor(res * ar + 0.5))
+            return (mx, mn) if width > height else (mn, mx)
+
+        P = lambda vs, fs, d=(): Program(js, vs, fs, d)
+        dye = Texture(self.dye.read.w, self.dye.read.h, 4, True); dye.data = self.dye.read.data
+        # ---- applyBloom(dye.read, bloom) ----------------------------------------------------------
+        bw, bh = get_resolution(c["BLOOM_RESOLUTION"])
+        bloom = Texture(bw, bh, 4, True)
+        pyramid = []
+        for i in range(c["BLOOM_ITERATIONS"]):
+            pw, ph = bw >> (i + 1), bh >> (i + 1)
+            if pw < 2 or ph < 2: break
+            pyramid.append(Texture(pw, ph, 4, True))
+        if len(pyramid) >= 2:
+            knee = c["BLOOM_THRESHOLD"] * c["BLOOM_SOFT_KNEE"] + 0.0001
+            pre = P("baseVertexShader", "bloomPrefilterShader")
+            pre.set(texelSize=(0.0, 0.0), curve=(c["BLOOM_THRESHOLD"] - knee, knee * 2, 0.25 / knee),
+                    threshold=c["BLOOM_THRESHOLD"], uTexture=dye)
+            pre.blit(bloom)
+            last = bloom
+            blurp = P("baseVertexShader", "bloomBlurShader")
+            for dest in pyramid:
+                blurp.set(texelSize=(last.texelSizeX, last.texelSizeY), uTexture=last)
+                blurp.blit(dest); last = dest
+            for i in range(len(pyramid) - 2, -1, -1):
+                base = pyramid[i]
+                blurp.set(texelSize=(last.texelSizeX, last.texelSizeY), uTexture=last)
+                blurp.blit(base, blend="add"); last = base
+            fin = P("baseVertexShader", "bloomFinalShader")
+            fin.set(texelSize=(last.texelSizeX, last.texelSizeY), uTexture=last, intensity=c["BLOOM_INTENSITY"])
+            fin.blit(bloom)
+        # ---- applySunrays(dye.read, dye.write, sunrays); blur(sunrays, sunraysTemp, 1) ---------------
+        sw, sh = get_resolution(c["SUNRAYS_RESOLUTION"])
+        mask = Texture(dye.w, dye.h, 4, True)
+        sun, tmp = Texture(sw, sh, 1, True), Texture(sw, sh, 1, True)
+        mp = P("baseVertexShader", "sunraysMaskShader"); mp.set(texelSize=(0.0, 0.0), uTexture=dye); mp.blit(mask)
+        sp = P("baseVertexShader", "sunraysShader"); sp.set(texelSize=(0.0, 0.0), weight=c["SUNRAYS_WEIGHT"], uTexture=mask); sp.blit(sun)
+        bp = P("blurVertexShader", "blurShader")
+        bp.set(texelSize=(sun.texelSizeX, 0.0), uTexture=sun); bp.blit(tmp)
+        bp.set(texelSize=(0.0, sun.texelSizeY), uTexture=tmp); bp.blit(sun)
+        # ---- drawColor + drawDisplay -------------------------------------------------------------------
+        target = Texture(width, height, 4, True)
+        col = P("baseVertexShader", "colorShader")
+        col.set(texelSize=(1.0 / width, 1.0 / height), color=(back_color[0] / 255, back_color[1] / 255, back_color[2] / 255, 1))
+        col.blit(target)
+        dith = Texture(dither.shape[1], dither.shape[0], 3, True, repeat=True)
+        dith.data[..., :3] = dither
+        disp = P("baseVertexShader", "displayShaderSource", ("SHADING", "BLOOM", "SUNRAYS"))
+        disp.set(texelSize=(1.0 / width, 1.0 / height), uTexture=dye, uBloom=bloom, uDithering=dith,
+                 ditherScale=(width / dith.w, height / dith.h), uSunrays=sun)          # S:1337-1346, S:1626-1631
+        disp.blit(target, blend="premult")
+        return dict(target=target.data.copy(), bloom=bloom.data.copy(), sunrays=sun.data[..., 0].copy(),
+                    mask_alpha=mask.data[..., 3].copy(), pyramid=[t.data.copy() for t in pyramid])
 
     # numpy views in this repo's array conventions
     def fields(self):

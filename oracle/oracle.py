@@ -160,6 +160,69 @@ def display(dye, w, h, shading=True, back_rgb=(0.0, 0.0, 0.0)):
     return out
 
 
+def render_postfx(dye, w, h, dither, cfg=None, back_rgb=(0.0, 0.0, 0.0)):
+    """render(null) with SHADING + BLOOM + SUNRAYS (reference desktop defaults S:70-84): applyBloom
+    (S:1350-1394), applySunrays + blur (S:1396-1419), drawColor + drawDisplay (S:1296-1348), FBO
+    sizes from getResolution (S:1012-1043).  ORACLE SIDE ONLY: no CUDA counterpart yet.
+    dither: (dh, dw, 3) float in [0,1], row 0 = first image row (no UNPACK_FLIP_Y)."""
+    L = lib(); i, f = C.c_int, C.c_float
+    L.oracle_bloom_prefilter.argtypes = [_f, i, i, _f, i, i, f, f, f, f]
+    L.oracle_box4.argtypes = [_f, i, i, _f, i, i, f, i]
+    L.oracle_sunrays_mask.argtypes = [_f, _f, i, i]
+    L.oracle_sunrays.argtypes = [_f, i, i, _f, i, i, f]
+    L.oracle_blur3.argtypes = [_f, _f, i, i, f, f]
+    L.oracle_display_full.argtypes = [_f, i, i, _f, i, i, _f, i, i, _f, i, i, _f, i, i, _f]
+    for fn in (L.oracle_bloom_prefilter, L.oracle_box4, L.oracle_sunrays_mask, L.oracle_sunrays, L.oracle_blur3,
+               L.oracle_display_full):
+        fn.restype = None
+    c = dict(BLOOM_ITERATIONS=8, BLOOM_RESOLUTION=256, BLOOM_INTENSITY=0.8, BLOOM_THRESHOLD=0.6,
+             BLOOM_SOFT_KNEE=0.7, SUNRAYS_RESOLUTION=196, SUNRAYS_WEIGHT=1.0)
+    c.update(cfg or {})
+    dye = _c(dye); Hd, Wd, _ = dye.shape
+    dither = _c(dither)
+
+    def get_resolution(res):                                  # S:1612-1624
+        ar = w / h
+        if ar < 1: ar = 1.0 / ar
+        mn, mx = int(np.floor(res + 0.5)), int(np.floor(res * ar + 0.5))
+        return (mx, mn) if w > h else (mn, mx)
+
+    bw, bh = get_resolution(c["BLOOM_RESOLUTION"])
+    bloom = np.zeros((bh, bw, 4), np.float32); bloom[..., 3] = 1.0        # createFBO clears to (0,0,0,1)
+    sizes = []
+    for k in range(c["BLOOM_ITERATIONS"]):
+        pw, ph = bw >> (k + 1), bh >> (k + 1)
+        if pw < 2 or ph < 2: break
+        sizes.append((pw, ph))
+    pyr = []
+    if len(sizes) >= 2:
+        knee = c["BLOOM_THRESHOLD"] * c["BLOOM_SOFT_KNEE"] + 0.0001
+        L.oracle_bloom_prefilter(_p(dye), Wd, Hd, _p(bloom), bw, bh, c["BLOOM_THRESHOLD"] - knee, knee * 2,
+                                 0.25 / knee, c["BLOOM_THRESHOLD"])
+        last, lw, lh = bloom, bw, bh
+        for pw, ph in sizes:
+            t = np.empty((ph, pw, 4), np.float32)
+            L.oracle_box4(_p(last), lw, lh, _p(t), pw, ph, 1.0, 0)
+            pyr.append(t); last, lw, lh = t, pw, ph
+        for k in range(len(pyr) - 2, -1, -1):
+            pw, ph = sizes[k]
+            L.oracle_box4(_p(last), lw, lh, _p(pyr[k]), pw, ph, 1.0, 1)
+            last, lw, lh = pyr[k], pw, ph
+        L.oracle_box4(_p(last), lw, lh, _p(bloom), bw, bh, c["BLOOM_INTENSITY"], 0)
+    sw, sh = get_resolution(c["SUNRAYS_RESOLUTION"])
+    mask = np.empty_like(dye)
+    L.oracle_sunrays_mask(_p(dye), _p(mask), Wd, Hd)
+    sun = np.empty((sh, sw), np.float32); tmp = np.empty_like(sun)
+    L.oracle_sunrays(_p(mask), Wd, Hd, _p(sun), sw, sh, c["SUNRAYS_WEIGHT"])
+    L.oracle_blur3(_p(sun), _p(tmp), sw, sh, 1.0 / sw, 0.0)
+    L.oracle_blur3(_p(tmp), _p(sun), sw, sh, 0.0, 1.0 / sh)
+    out = np.empty((h, w, 4), np.float32)
+    back = np.asarray(back_rgb, np.float32)
+    L.oracle_display_full(_p(dye), Wd, Hd, _p(bloom), bw, bh, _p(sun), sw, sh, _p(dither), dither.shape[1],
+                          dither.shape[0], _p(out), w, h, _p(back))
+    return dict(target=out, bloom=bloom, sunrays=sun, mask_alpha=mask[..., 3].copy(), pyramid=pyr)
+
+
 def round_half(a):
     a = _c(a).copy()
     lib().oracle_round_half(_p(a), a.size)

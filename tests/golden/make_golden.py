@@ -104,7 +104,29 @@ def display(name, Wd, Hd, w, h, seed):
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **o)
 
 
+def postfx(name, Wd, Hd, w, h, seed, bloom_res=64, sun_res=48):
+    """render(null) with SHADING + BLOOM + SUNRAYS: the executed bloom / sunrays / blur / display
+    shaders with the reference's FBO pyramid and blending.  The dithering texture is decoded from
+    the reference's LDR_LLL1_0.png here and stored in the fixture (row 0 = first image row)."""
+    from PIL import Image
+    dither = np.asarray(Image.open("/root/reference/LDR_LLL1_0.png").convert("RGB"), dtype=np.float32) / np.float32(255.0)
+    rng = np.random.default_rng(seed)
+    s = G.GLSLSim(16, 16, Wd, Hd)
+    dye = (rng.random((Hd, Wd, 4), dtype=np.float32) ** 4 * 3).astype(np.float32); dye[..., 3] = 1
+    s.load(dye=dye)
+    # small FBOs keep the fixture small; the chain (prefilter, pyramid down / additive up, final,
+    # mask, march, blur, display) is the same as with the 256 / 196 defaults
+    r = s.render_postfx(w, h, dither, cfg=dict(BLOOM_RESOLUTION=bloom_res, SUNRAYS_RESOLUTION=sun_res), back_color=(10, 20, 30))
+    o = dict(Wd=Wd, Hd=Hd, w=w, h=h, bloom_res=bloom_res, sun_res=sun_res, in_dye=dye, dither=dither.astype(np.float16), back=np.array([10, 20, 30], np.float32),
+             target=r["target"], bloom=r["bloom"].astype(np.float32), sunrays=r["sunrays"], mask_alpha=r["mask_alpha"])
+    for k, t in enumerate(r["pyramid"]):
+        o[f"pyr{k}"] = t
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **o)
+
+
 if __name__ == "__main__":
+    postfx("postfx_64_to_128", 64, 64, 128, 128, 21)           # power-of-two target, dye and bloom FBO
+    postfx("postfx_48x32_to_50x75", 48, 32, 50, 75, 22)        # ragged, portrait canvas
     display("display_64_to_128", 64, 64, 128, 128, 11)      # power-of-two target: bitwise
     display("display_40x28_to_50x30", 40, 28, 50, 30, 12)   # ragged: vUv rounding -> tolerance
     per_pass(32, 32, 64, 64, 1)

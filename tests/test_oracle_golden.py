@@ -110,3 +110,27 @@ def test_display_matches_executed_reference_shaders(oracle, name, exact):
             assert bits_equal(got, g[key]), key
         else:
             assert max_rel(got, g[key]) < 1e-5, key
+
+
+@pytest.mark.parametrize("name,pow2", [("postfx_64_to_128", True), ("postfx_48x32_to_50x75", False)])
+def test_postfx_chain_matches_executed_reference_shaders(oracle, name, pow2):
+    """Oracle side of SURVEY 8f rank 1, second half (no CUDA yet): bloom prefilter + 7-level pyramid
+    with additive up-sampling + final, sunrays mask / 16-step march / separable blur, and the full
+    display shader (SHADING + BLOOM + SUNRAYS, dithering texture, gamma), against the executed
+    shaders.  Power-of-two sizes: the bloom chain and the mask are bit-identical; the sunrays FBO is
+    48 wide here (196 by default — never a power of two) and pow() is implementation-defined, hence the small tolerances."""
+    g = golden(name); O = oracle
+    dither = g["dither"].astype(np.float32)
+    r = O.render_postfx(g["in_dye"], int(g["w"]), int(g["h"]), dither,
+                        cfg=dict(BLOOM_RESOLUTION=int(g["bloom_res"]), SUNRAYS_RESOLUTION=int(g["sun_res"])),
+                        back_rgb=tuple(float(x) / 255 for x in g["back"]))
+    n = len([k for k in g.files if k.startswith("pyr")])
+    assert len(r["pyramid"]) == n
+    if pow2:
+        assert bits_equal(r["bloom"], g["bloom"]) and bits_equal(r["mask_alpha"], g["mask_alpha"])
+        assert all(bits_equal(r["pyramid"][k], g[f"pyr{k}"]) for k in range(n))
+        assert max_rel(r["sunrays"], g["sunrays"]) < 2e-6 and max_rel(r["target"], g["target"]) < 2e-6
+    else:
+        tol = 3e-4                      # vUv rounding on ragged grids, amplified by br * 20 in the mask
+        assert max_rel(r["bloom"], g["bloom"]) < tol and max_rel(r["mask_alpha"], g["mask_alpha"]) < tol
+        assert max_rel(r["sunrays"], g["sunrays"]) < tol and max_rel(r["target"], g["target"]) < tol
