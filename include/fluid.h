@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define FLUID_ABI_VERSION 1
+#define FLUID_ABI_VERSION 2
 
 typedef struct fluid fluid_t; /* opaque; owns device buffers, streams, events, graphs, NCCL comm */
 
@@ -149,6 +149,10 @@ int fluid_splat(fluid_t* h, float x, float y, float dx, float dy, float r, float
 /* config.<KEY> = value (S:59-69).  PRESSURE_ITERATIONS / JACOBI_BLOCK are rounded to int. */
 int fluid_set_param(fluid_t* h, int key, float value);
 int fluid_get_param(fluid_t* h, int key, float* value);
+/* Same as fluid_set_param, at the precision the JS `config` values have.  SPLAT_RADIUS and ASPECT
+ * enter DOUBLE arithmetic on the host (correctRadius(config.SPLAT_RADIUS / 100.0), S:1447 +
+ * S:1457-1462) before the one narrowing of gl.uniform1f; host mirrors should use this entry point. */
+int fluid_set_param_f64(fluid_t* h, int key, double value);
 
 /* ---- individual passes (the reference's one-blit-per-program granularity; used by the parity
  *      tests and by callers that drive the loop themselves).  Each reads the `.read` buffers and
@@ -201,6 +205,18 @@ int fluid_elapsed_ms(fluid_t* h, float* ms);
 /* Number of CUDA kernels this handle has launched since creation (graph replays count their
  * kernel nodes). */
 uint64_t fluid_launch_count(fluid_t* h);
+
+/* Counters since creation (no reference counterpart; bench.py and the tests read them). */
+typedef enum fluid_stat_key {
+    FLUID_STAT_LAUNCHES = 0,         /* == fluid_launch_count                                        */
+    FLUID_STAT_JACOBI_LAUNCHES = 1,  /* Jacobi kernels only (graph replays count their kernel nodes)  */
+    FLUID_STAT_HALO_LAUNCHES = 2,    /* halo_push / halo_wait kernels of the peer-memory transport    */
+    FLUID_STAT_HALO_EXCHANGES = 3,   /* halo exchanges issued (either transport)                      */
+    FLUID_STAT_GRAPH_CAPTURES = 4,   /* step() graphs captured + instantiated                         */
+    FLUID_STAT_GRAPH_LAUNCHES = 5,   /* step() graphs replayed                                        */
+    FLUID_STAT_HALO_TRANSPORT_P2P = 6 /* 1 when the peer-memory halo path is active                    */
+} fluid_stat_key;
+uint64_t fluid_stat(fluid_t* h, int key);
 
 /* Raw device pointer of a field's `.read` buffer (for zero-copy interop, e.g. torch.as_tensor
  * through __cuda_array_interface__); valid until the next call that swaps that field. */

@@ -138,6 +138,13 @@ void oracle_jacobi(const float* p, const float* div, float* pout, int W, int H) 
     }
 }
 
+/* Row-parallel copy with the SAME static row schedule as the passes: timing legs use it to
+ * first-touch their buffers on the threads (NUMA nodes) that will later sweep those rows. */
+void oracle_copy_rows(float* dst, const float* src, int W, int H) {
+#pragma omp parallel for schedule(static)
+    for (int j = 0; j < H; ++j) memcpy(dst + (size_t)j * W, src + (size_t)j * W, (size_t)W * sizeof(float));
+}
+
 void oracle_jacobi_iters(float* p, float* tmp, const float* div, int W, int H, int iters) {
     float *a = p, *b = tmp;
     for (int k = 0; k < iters; ++k) {
@@ -237,20 +244,6 @@ void oracle_splat(const float* base, float* out, int W, int H, int C, float aspe
     }
 }
 
-/* copyShader S:496-506 drawn into the new FBO while sampling the old texture through its
- * LINEAR filter (resizeFBO S:1108-1114).  Bilinear is defined as in bilerp above. */
-void oracle_resample(const float* src, int Ws, int Hs, float* dst, int Wd, int Hd, int C) {
-    const float tsx = (float)(1.0 / (double)Ws), tsy = (float)(1.0 / (double)Hs);
-#pragma omp parallel for schedule(static)
-    for (int J = 0; J < Hd; ++J) {
-        const float uvy = ((float)J + 0.5f) / (float)Hd;
-        for (int I = 0; I < Wd; ++I) {
-            const float uvx = ((float)I + 0.5f) / (float)Wd;
-            bilerp(src, Ws, Hs, C, uvx, uvy, tsx, tsy, dst + ((size_t)J * Wd + I) * C);
-        }
-    }
-}
-
 /* GL_LINEAR + CLAMP_TO_EDGE fetch as the GL ES 2.0 spec (3.7.7) writes it: u' = u*W - 0.5,
  * i0 = floor(u'), alpha = frac(u'); tau = (1-a)(1-b) t00 + a(1-b) t10 + (1-a) b t01 + a b t11. */
 static inline void linear_fetch(const float* tex, int W, int H, int C, float uvx, float uvy, float* out) {
@@ -263,6 +256,21 @@ static inline void linear_fetch(const float* tex, int W, int H, int C, float uvx
     const float* t00 = tex + ((size_t)j0 * W + i0) * C; const float* t10 = tex + ((size_t)j0 * W + i1) * C;
     const float* t01 = tex + ((size_t)j1 * W + i0) * C; const float* t11 = tex + ((size_t)j1 * W + i1) * C;
     for (int k = 0; k < C; ++k) out[k] = ((w00 * t00[k] + w10 * t10[k]) + w01 * t01[k]) + w11 * t11[k];
+}
+
+/* copyShader S:496-506 drawn into the new FBO while sampling the old texture through its
+ * LINEAR filter (resizeFBO S:1108-1114): a sampler fetch, so the GL-spec weight form of
+ * linear_fetch above (the same one the display pass uses), pinned by the executed copyShader
+ * golden tests/golden/resample_*.npz. */
+void oracle_resample(const float* src, int Ws, int Hs, float* dst, int Wd, int Hd, int C) {
+#pragma omp parallel for schedule(static)
+    for (int J = 0; J < Hd; ++J) {
+        const float uvy = ((float)J + 0.5f) / (float)Hd;
+        for (int I = 0; I < Wd; ++I) {
+            const float uvx = ((float)I + 0.5f) / (float)Wd;
+            linear_fetch(src, Ws, Hs, C, uvx, uvy, dst + ((size_t)J * Wd + I) * C);
+        }
+    }
 }
 
 /* render(target) with BLOOM and SUNRAYS off, TRANSPARENT off (S:1296-1317): drawColor(BACK_COLOR)

@@ -32,6 +32,7 @@ void oracle_clear(const float* in, float* out, size_t n, float value);
 /* pressureShader S:868-890: ONE Jacobi sweep */
 void oracle_jacobi(const float* p, const float* div, float* pout, int W, int H);
 /* the loop S:1259-1266: result is left in p (tmp is scratch of the same size) */
+void oracle_copy_rows(float* dst, const float* src, int W, int H);
 void oracle_jacobi_iters(float* p, float* tmp, const float* div, int W, int H, int iters);
 /* gradientSubtractShader S:892-913 */
 void oracle_gradient_subtract(const float* p, const float* v, float* vout, int W, int H);

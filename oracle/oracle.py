@@ -43,6 +43,7 @@ def lib():
         L.oracle_clear.argtypes = [_f, _f, sz, f]
         L.oracle_jacobi.argtypes = [_f, _f, _f, i, i]
         L.oracle_jacobi_iters.argtypes = [_f, _f, _f, i, i, i]
+        L.oracle_copy_rows.argtypes = [_f, _f, i, i]; L.oracle_copy_rows.restype = None
         L.oracle_gradient_subtract.argtypes = [_f, _f, _f, i, i]
         L.oracle_advect.argtypes = [_f, i, i, _f, _f, i, i, i, f, f]
         L.oracle_splat.argtypes = [_f, _f, i, i, i, f, f, f, _f, f]
@@ -71,12 +72,36 @@ def num_threads() -> int:
     return int(lib().oracle_num_threads())
 
 
-def use_all_cores() -> int:
-    """Size the OpenMP team to the cores this process may run on (torchrun sets OMP_NUM_THREADS=1)."""
+def usable_cores() -> int:
+    """Cores this process can actually USE: the affinity mask, capped by the cgroup CPU quota
+    (a container may see 128 CPUs in its mask and be throttled to a few cores' worth of time —
+    an OpenMP team sized by the mask then runs 10-100x slower and erratically)."""
     try:
         n = len(os.sched_getaffinity(0))
     except AttributeError:
         n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(float(txt[0]) / float(txt[1]) + 0.5)))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                    n = min(n, max(1, int(q / per + 0.5)))
+            break
+        except Exception:
+            continue
+    return n
+
+
+def use_all_cores(n: int | None = None) -> int:
+    """Size the OpenMP team to the cores this process may use (torchrun sets OMP_NUM_THREADS=1).
+    Pass `n` when the count was taken earlier: with OMP_PROC_BIND set, an OpenMP runtime binds the
+    initial thread when it loads, after which the affinity mask of this thread is a single core."""
+    n = usable_cores() if n is None else int(n)
     L = lib()
     L.oracle_set_num_threads.argtypes = [C.c_int]; L.oracle_set_num_threads.restype = None
     L.oracle_set_num_threads(int(n))
@@ -231,10 +256,10 @@ def round_half(a):
 
 def correct_radius(splat_radius: float, aspect: float) -> np.float32:
     """correctRadius(config.SPLAT_RADIUS / 100.0), S:1447 + S:1457-1462 (double math, fp32 uniform)."""
-    r = float(np.float32(splat_radius)) / 100.0
+    r = float(splat_radius) / 100.0          # JS doubles all the way ...
     if aspect > 1:
-        r *= float(np.float32(aspect))
-    return np.float32(r)
+        r *= float(aspect)
+    return np.float32(r)                     # ... narrowed once, by gl.uniform1f
 
 
 class OracleSim:

@@ -124,7 +124,35 @@ def postfx(name, Wd, Hd, w, h, seed, bloom_res=64, sun_res=48):
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **o)
 
 
+def resample(name, Ws, Hs, Wd, Hd, ch, seed):
+    """resizeFBO (S:1108-1114): the executed copyShader (S:496-506) drawn into a new Wd x Hd FBO
+    while sampling the old Ws x Hs texture through its LINEAR filter (`filtering` of S:988 on the
+    default desktop path; the NEAREST variant is stored too for reference)."""
+    js = open(G.REFERENCE_JS).read()
+    rng = np.random.default_rng(seed)
+    src = (rng.standard_normal((Hs, Ws, ch)) * 3).astype(np.float32)
+    o = dict(Ws=Ws, Hs=Hs, Wd=Wd, Hd=Hd, ch=ch, src=src)
+    for tag, lin in (("linear", True), ("nearest", False)):
+        old = G.Texture(Ws, Hs, ch, lin)
+        old.store(G.V(np.concatenate([src, np.zeros((Hs, Ws, 4 - ch), np.float32)], axis=-1)))
+        new = G.Texture(Wd, Hd, ch, lin)
+        prog = G.Program(js, "baseVertexShader", "copyShader")
+        prog.set(uTexture=old, texelSize=(0.0, 0.0))   # copyProgram never sets texelSize (S:1111): default 0
+        prog.blit(new)
+        o[tag] = new.data[..., :ch].copy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **o)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "r02":     # the vectors added in round 2 only
+        resample("resample_v_32_to_48", 32, 32, 48, 48, 2, 31)           # up-sample, ragged ratio
+        resample("resample_dye_64_to_32", 64, 64, 32, 32, 4, 32)         # down-sample by 2 (power of two)
+        resample("resample_dye_40x28_to_64x48", 40, 28, 64, 48, 4, 33)
+        # BASELINE configs[0]: 128x128 sim / 256x256 dye, 20 iterations (the reference's own defaults
+        # except the dye size) -- two whole steps after multipleSplats(5)
+        scenario("config0_128_256", 128, 128, 256, 256, 5, 2, dict(CURL=30, PRESSURE_ITERATIONS=20), 4321)
+        print("round-2 golden vectors written to", OUT)
+        sys.exit(0)
     postfx("postfx_64_to_128", 64, 64, 128, 128, 21)           # power-of-two target, dye and bloom FBO
     postfx("postfx_48x32_to_50x75", 48, 32, 50, 75, 22)        # ragged, portrait canvas
     display("display_64_to_128", 64, 64, 128, 128, 11)      # power-of-two target: bitwise

@@ -27,7 +27,7 @@ def test_header_and_library_agree(L):
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for s in declared:
         assert hasattr(L, s), s
-    assert L.fluid_abi_version() == 1
+    assert L.fluid_abi_version() == 2
 
 
 def test_no_torch_types_in_the_abi():

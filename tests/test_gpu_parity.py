@@ -174,16 +174,94 @@ def test_properties_at_full_size_4096(pkg):
     p = rng.standard_normal((H, W)).astype(np.float32)
     d = rng.uniform(-1, 1, (H, W)).astype(np.float32)
 
-    def solve(pp, dd, flags=0, jb=8):
-        s = make(pkg, W, H, 64, 64, flags=flags, jb=jb, PRESSURE_ITERATIONS=iters, PRESSURE=1.0)
+    def solve(pp, dd, flags=0, jb=0, pressure=0.8):
+        # jb = 0: the library's default block depth, PRESSURE 0.8 with the clear pass fused into the
+        # first launch -- exactly the configuration bench.py times
+        s = make(pkg, W, H, 64, 64, flags=flags, jb=jb, PRESSURE_ITERATIONS=iters, PRESSURE=pressure)
         s.writeField("pressure", pp); s.writeField("divergence", dd)
         s.pass_("pressure_solve"); out = s.readField("pressure"); s.close()
         return out
     a = solve(p, d)
     assert bits_equal(a, solve(p, d, flags=pkg.FLAG_NAIVE_JACOBI, jb=1))
+    assert bits_equal(a, solve(p, d, jb=8))                           # another block depth, same bits
     assert bits_equal(solve(4 * p, 4 * d), 4 * a)
-    assert bits_equal(solve(np.full_like(p, 2.5), np.zeros_like(d)), np.full_like(p, 2.5))
+    assert bits_equal(solve(np.full_like(p, 2.5), np.zeros_like(d), pressure=1.0), np.full_like(p, 2.5))
     assert bits_equal(solve(p[:, ::-1].copy(), d[:, ::-1].copy()), a[:, ::-1])
+    # a slice of the full-size result against the oracle: the Jacobi stencil's cone of influence is
+    # `iters` cells, so rows [0, 192) of the solve depend only on rows [0, 192 + iters) of the input
+    # with the true bottom wall -- recompute that strip on the CPU and compare the part that is exact
+    from oracle import oracle as O
+    strip = 192 + iters
+    ref = O.jacobi(O.clear(p[:strip], 0.8), d[:strip], iters)
+    assert bits_equal(a[:192], ref[:192])
+
+
+def test_config0_whole_steps_vs_executed_reference_and_oracle(pkg, oracle):
+    """BASELINE configs[0]: 128x128 sim / 256x256 dye, 20 iterations.  (a) two whole steps after
+    multipleSplats(5) against the golden cut from the executed reference shaders (tolerances as in
+    tests/test_oracle_golden.py: splat expf last place, amplified by vorticity confinement);
+    (b) from written (not splatted) fields: 4 whole steps bit-identical to the oracle."""
+    g = golden("config0_128_256")
+    s = make(pkg, 128, 128, 256, 256, CURL=30, PRESSURE_ITERATIONS=20)
+    for a in g["splats"]:
+        s.splat(*[float(x) for x in a[:4]], tuple(float(x) for x in a[4:]))
+    for k, tol in ((1, 1e-5), (2, 5e-5)):
+        s.step(float(g["dt"]))
+        for n in ("velocity", "dye", "pressure", "divergence", "curl"):
+            assert max_rel(s.readField(n), g[f"s{k}_{n}"]) < tol, (k, n)
+    s.close()
+    O = oracle
+    v, dye, p = rand_fields(128, 128, 256, 256, 17)
+    s = make(pkg, 128, 128, 256, 256, PRESSURE_ITERATIONS=20)
+    ref = O.OracleSim(128, 128, 256, 256)
+    s.writeField("velocity", v); s.writeField("dye", dye); s.writeField("pressure", p)
+    ref.velocity, ref.dye, ref.pressure = v.copy(), dye.copy(), p.copy()
+    for _ in range(4):
+        s.step(DT); ref.step(DT)
+    for n in ("velocity", "dye", "pressure", "divergence", "curl"):
+        assert bits_equal(s.readField(n), getattr(ref, n)), n
+    s.close()
+
+
+def test_config1_whole_steps_bitwise_vs_oracle(pkg, oracle):
+    """BASELINE configs[1]: 1024x1024 sim / 2048x2048 dye, 30 iterations, fp32: two whole steps from
+    written fields, every field bit-identical to the CPU oracle (graph replay, fused kernels,
+    temporally blocked Jacobi at its default depth)."""
+    O = oracle
+    W = H = 1024; Wd = Hd = 2048
+    v, dye, p = rand_fields(W, H, Wd, Hd, 5)
+    s = make(pkg, W, H, Wd, Hd, PRESSURE_ITERATIONS=30)
+    ref = O.OracleSim(W, H, Wd, Hd, PRESSURE_ITERATIONS=30)
+    s.writeField("velocity", v); s.writeField("dye", dye); s.writeField("pressure", p)
+    ref.velocity, ref.dye, ref.pressure = v.copy(), dye.copy(), p.copy()
+    for _ in range(2):
+        s.step(DT); ref.step(DT)
+    for n in ("velocity", "dye", "pressure", "divergence", "curl"):
+        assert bits_equal(s.readField(n), getattr(ref, n)), n
+    s.close()
+
+
+def test_update_loop_with_jittered_dt_replays_two_graphs(pkg):
+    """calcDeltaTime() (S:1188-1194) yields a different dt on every frame; dt lives in device
+    memory, so 200 update() calls replay the same two instantiated graphs (one per ping-pong
+    parity) and stay bit-identical to the pass-by-pass path."""
+    W = H = 128; Wd = Hd = 256
+    v, dye, p = rand_fields(W, H, Wd, Hd, 33)
+    sims = [make(pkg, W, H, Wd, Hd, flags=f) for f in (0, pkg.FLAG_NO_GRAPH)]
+    for s in sims:
+        s.writeField("velocity", v); s.writeField("dye", dye); s.writeField("pressure", p)
+        s.lastUpdateTime = 0.0
+    rng = np.random.default_rng(8)
+    now = 0.0
+    for k in range(200):
+        now += float(rng.uniform(3.0, 21.0))          # ms between frames: mostly below the 16.666 ms clamp
+        for s in sims:
+            s.update(now_ms=now)
+    assert sims[0].stat("graph_captures") <= 2 and sims[0].stat("graph_launches") == 200
+    for n in ("velocity", "dye", "pressure"):
+        assert bits_equal(sims[0].readField(n), sims[1].readField(n)), n
+    for s in sims:
+        s.close()
 
 
 def test_host_pressure_solve_matches_resident_path(pkg):
@@ -211,6 +289,13 @@ def test_resize_carries_state_like_resizeDoubleFBO(pkg, oracle):
     assert bits_equal(s.readField("velocity"), O.resample(v, 48, 48))
     assert bits_equal(s.readField("dye"), O.resample(dye, 96, 96))
     assert not s.readField("pressure").any() and not s.readField("divergence").any()
+    s.close()
+    # and straight against the executed copyShader (power-of-two sizes: bitwise)
+    g = golden("resample_dye_64_to_32")
+    s = make(pkg, 16, 16, 64, 64)
+    s.writeField("dye", g["src"])
+    s._sizes = (16, 16, 32, 32); s.initFramebuffers()
+    assert bits_equal(s.readField("dye"), g["linear"])
     s.close()
 
 

@@ -134,3 +134,31 @@ def test_postfx_chain_matches_executed_reference_shaders(oracle, name, pow2):
         tol = 3e-4                      # vUv rounding on ragged grids, amplified by br * 20 in the mask
         assert max_rel(r["bloom"], g["bloom"]) < tol and max_rel(r["mask_alpha"], g["mask_alpha"]) < tol
         assert max_rel(r["sunrays"], g["sunrays"]) < tol and max_rel(r["target"], g["target"]) < tol
+
+
+@pytest.mark.parametrize("name,exact", [("resample_dye_64_to_32", True), ("resample_v_32_to_48", False),
+                                        ("resample_dye_40x28_to_64x48", False)])
+def test_resample_matches_executed_copy_shader(oracle, name, exact):
+    """resizeFBO (S:1108-1114): oracle_resample against the executed copyShader drawn through a
+    LINEAR sampler.  Power-of-two sizes: bit-identical; otherwise the rasteriser's interpolated vUv
+    differs from (i+.5)/W in the last place, which moves the weights (value-level agreement)."""
+    g = golden(name)
+    got = oracle.resample(g["src"], int(g["Wd"]), int(g["Hd"]))
+    if exact:
+        assert bits_equal(got, g["linear"])
+    else:
+        assert max_rel(got, g["linear"]) < 2e-6
+
+
+def test_config0_matches_reference_orchestration(oracle):
+    """BASELINE configs[0] (128x128 sim / 256x256 dye, 20 Jacobi iterations): two whole steps after
+    multipleSplats(5), against the executed reference shaders.  Step 1 at the P2 tolerance 1e-5
+    (SURVEY §8c); step 2 at 5e-5: the only difference between the two runs is exp()'s last place in
+    the splats (1.5e-7 of the field), which vorticity confinement's force/(|force|+1e-4) amplifies
+    by ~10x per step on the divergence (measured: 1.7e-6 after one step, 2.5e-5 after two)."""
+    g = golden("config0_128_256"); O = oracle
+    s = _run_scenario(O, g, O.OracleSim)
+    for k, tol in ((1, 1e-5), (2, 5e-5)):
+        s.step(float(g["dt"]))
+        for n in ("velocity", "dye", "pressure", "divergence", "curl"):
+            assert max_rel(getattr(s, n), g[f"s{k}_{n}"]) < tol, (k, n)

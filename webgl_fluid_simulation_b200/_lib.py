@@ -17,7 +17,7 @@ CSRC = os.path.join(_HERE, "csrc")
 SYMBOLS = [
     "fluid_abi_version", "fluid_config_default", "fluid_get_resolution", "fluid_create",
     "fluid_create_slab", "fluid_nccl_unique_id", "fluid_p2p_export", "fluid_p2p_connect", "fluid_p2p_disable", "fluid_destroy", "fluid_resize", "fluid_step",
-    "fluid_splat", "fluid_set_param", "fluid_get_param", "fluid_pass_curl", "fluid_pass_vorticity",
+    "fluid_splat", "fluid_set_param", "fluid_set_param_f64", "fluid_get_param", "fluid_stat", "fluid_pass_curl", "fluid_pass_vorticity",
     "fluid_pass_divergence", "fluid_pass_clear_pressure", "fluid_pass_jacobi",
     "fluid_pass_pressure_solve", "fluid_pass_gradient_subtract", "fluid_pass_advect_velocity",
     "fluid_pass_advect_dye", "fluid_pass_curl_vorticity_divergence", "fluid_field_elems",
@@ -34,6 +34,8 @@ FIELD = {"velocity": 0, "dye": 1, "pressure": 2, "divergence": 3, "curl": 4}
 PARAM = {"DENSITY_DISSIPATION": 0, "VELOCITY_DISSIPATION": 1, "PRESSURE": 2,
          "PRESSURE_ITERATIONS": 3, "CURL": 4, "SPLAT_RADIUS": 5, "ASPECT": 6, "JACOBI_BLOCK": 7}
 FLAG_UNFUSED, FLAG_NO_GRAPH, FLAG_NAIVE_JACOBI = 0x1, 0x2, 0x4
+STAT = {"launches": 0, "jacobi_launches": 1, "halo_launches": 2, "halo_exchanges": 3,
+        "graph_captures": 4, "graph_launches": 5, "halo_transport_p2p": 6}
 
 
 class FluidError(RuntimeError):
@@ -93,7 +95,9 @@ def lib():
     L.fluid_step.argtypes = [vp, f]
     L.fluid_splat.argtypes = [vp] + [f] * 7
     L.fluid_set_param.argtypes = [vp, i, f]
+    L.fluid_set_param_f64.argtypes = [vp, i, C.c_double]
     L.fluid_get_param.argtypes = [vp, i, fp]
+    L.fluid_stat.argtypes = [vp, i]; L.fluid_stat.restype = C.c_uint64
     for n in ("curl", "divergence", "clear_pressure", "pressure_solve", "gradient_subtract"):
         getattr(L, "fluid_pass_" + n).argtypes = [vp]
     for n in ("vorticity", "advect_velocity", "advect_dye", "curl_vorticity_divergence"):

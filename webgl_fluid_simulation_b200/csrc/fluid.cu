@@ -44,6 +44,11 @@ struct fluid {
     float* curl = nullptr;
     int* halo_flag = nullptr;        // device flag set by advection when a tap leaves the ghost zone
     uint64_t launches = 0;
+    uint64_t jacobi_kernel_launches = 0;   // Jacobi kernels only (fluid_stat FLUID_STAT_JACOBI_LAUNCHES)
+    uint64_t halo_kernel_launches = 0;     // halo_push / halo_wait kernels of the peer-memory transport
+    float* dt_dev = nullptr;               // step()'s dt lives in device memory: one graph serves every dt
+    double splat_radius_d = 0.25;          // config.SPLAT_RADIUS and the canvas aspect as the JS doubles they are
+    double aspect_d = 1.0;                 // (correctRadius S:1457-1462 is double arithmetic, narrowed once)
     fluid_timing timing{};
     bool have_timing = false;
     std::string err;
@@ -91,6 +96,7 @@ inline void swap_p(fluid_t* h) { h->pressure.swap(); h->par_p ^= 1; }
 inline void swap_dye(fluid_t* h) { h->dye.swap(); h->par_dye ^= 1; }
 
 void drop_graphs(fluid_t* h) {
+    if (!h->graphs.empty() && h->stream) cudaStreamSynchronize(h->stream);   // an exec may still be in flight
     for (auto& kv : h->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     h->graphs.clear();
 }
@@ -140,6 +146,15 @@ int check_launch(fluid_t* h, const char* what, int n = 1) {
     return FLUID_OK;
 }
 
+// dt of the current step()/pass, in device memory.  Stream-ordered 4-byte upload from a pageable
+// host word (the driver stages it before returning), issued OUTSIDE any capture: an instantiated
+// step graph therefore never bakes dt in, and the reference's calcDeltaTime() (S:1188-1194, a new
+// dt every frame) replays the same graph.
+int set_dt(fluid_t* h, float dt) {
+    CU(cudaMemcpyAsync(h->dt_dev, &dt, sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    return FLUID_OK;
+}
+
 #include "halo.cuh"
 
 // ---- Jacobi dispatch -----------------------------------------------------------------------------
@@ -157,6 +172,7 @@ int launch_tb(fluid_t* h, const JacobiArgs& a) {
     static const bool tma = getenv("FLUID_TB_STAGE") && !strcmp(getenv("FLUID_TB_STAGE"), "tma");
     if (tma) jacobi_tb_kernel<K, SCALE, true><<<nxw * nch, 32, T::SMEM, h->stream>>>(a);   // one warp per CTA
     else jacobi_tb_kernel<K, SCALE, false><<<nxw * nch, 32, T::SMEM, h->stream>>>(a);
+    ++h->jacobi_kernel_launches;
     return check_launch(h, "jacobi_tb_kernel");
 }
 
@@ -273,10 +289,12 @@ int run_jacobi(fluid_t* h, int iters, bool scale_first, int* launches_out) {
             dim3 g((W / 4 + b.x - 1) / b.x, (a.out_hi - a.out_lo + b.y - 1) / b.y);
             if (sc) jacobi_sweep_kernel<true><<<g, b, 0, h->stream>>>(a);
             else jacobi_sweep_kernel<false><<<g, b, 0, h->stream>>>(a);
+            ++h->jacobi_kernel_launches;
             rc = check_launch(h, "jacobi_sweep_kernel");
         } else {
             dim3 b(64, 4);
             jacobi_scalar_kernel<<<grid2d(W, a.out_hi - a.out_lo, b), b, 0, h->stream>>>(a, sc);
+            ++h->jacobi_kernel_launches;
             rc = check_launch(h, "jacobi_scalar_kernel");
         }
         if (rc) return rc;
@@ -360,6 +378,7 @@ int check_halo(fluid_t* h) {
     int flag = 0;
     CU(cudaMemcpyAsync(&flag, h->halo_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    if (flag) CU(cudaMemsetAsync(h->halo_flag, 0, sizeof(int), h->stream));   // report once; the caller decides what to do next
     if (flag == 2)
         return fail(h, FLUID_ERR_HALO, "peer-memory halo exchange timed out waiting for a neighbour rank");
     if (flag == 3)
@@ -403,6 +422,8 @@ int create_common(const fluid_config* cfg, int rank, int world, const void* uid,
     h->device = dev;
     h->sm_count = prop.multiProcessorCount;
     if (!(h->cfg.aspect > 0.0f)) h->cfg.aspect = (float)((double)cfg->sim_w / (double)cfg->sim_h);
+    h->aspect_d = (cfg->aspect > 0.0f) ? (double)cfg->aspect : (double)cfg->sim_w / (double)cfg->sim_h;
+    h->splat_radius_d = (double)cfg->splat_radius;
     h->rank = rank; h->world = world;
     const int H = cfg->sim_h, Hd = cfg->dye_h;
     h->row0 = (int)((long long)H * rank / world);  h->row1 = (int)((long long)H * (rank + 1) / world);
@@ -431,6 +452,8 @@ int create_common(const fluid_config* cfg, int rank, int world, const void* uid,
         for (auto& e : h->tev) CU(cudaEventCreate(&e));
         CU(cudaMalloc((void**)&h->halo_flag, sizeof(int)));
         CU(cudaMemsetAsync(h->halo_flag, 0, sizeof(int), h->stream));
+        CU(cudaMalloc((void**)&h->dt_dev, sizeof(float)));
+        CU(cudaMemsetAsync(h->dt_dev, 0, sizeof(float), h->stream));
         int r = alloc_fields(h); if (r) return r;
         CU(cudaStreamSynchronize(h->stream));
         if (world > 1) {
@@ -517,6 +540,11 @@ static_assert(sizeof(P2PBlob) == 256, "blob layout");
 int fluid_p2p_export(fluid_t* h, void* blob, size_t blob_bytes) {
     if (!h || !blob || blob_bytes < sizeof(P2PBlob)) return fail(h, FLUID_ERR_INVALID, "blob must hold 256 bytes");
     if (!h->slab() || !h->arena) return fail(h, FLUID_ERR_INVALID, "fluid_p2p_export needs a slab handle");
+    // halo_push_kernel moves rows as 16-byte words: every exchanged row (4*W pressure / divergence,
+    // 8*W velocity, 16*Wd dye) must be a multiple of 16 bytes.  Otherwise refuse, so that the
+    // launcher keeps ALL ranks on the byte-exact NCCL transport.
+    if (h->cfg.sim_w % 4 != 0)
+        return fail(h, FLUID_ERR_INVALID, "peer-memory halos need sim width %% 4 == 0 (got %d): staying on NCCL", h->cfg.sim_w);
     P2PBlob b{};
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaIpcGetMemHandle(&b.mem, h->arena));
@@ -572,6 +600,7 @@ void fluid_destroy(fluid_t* h) {
     }
     free_fields(h);
     cudaFree(h->halo_flag);
+    cudaFree(h->dt_dev);
     cudaFree(h->frame);
     if (h->comm) { ncdl::api().CommDestroy(h->comm); h->comm = nullptr; }
     for (auto& e : h->mark) if (e) cudaEventDestroy(e);
@@ -588,11 +617,23 @@ int fluid_set_param(fluid_t* h, int key, float v) {
         case FLUID_PRESSURE: h->cfg.pressure = v; break;
         case FLUID_PRESSURE_ITERATIONS: h->cfg.pressure_iterations = (int)(v + 0.5f); break;
         case FLUID_CURL: h->cfg.curl = v; break;
-        case FLUID_SPLAT_RADIUS: h->cfg.splat_radius = v; break;
-        case FLUID_ASPECT: h->cfg.aspect = v; break;
+        case FLUID_SPLAT_RADIUS: h->cfg.splat_radius = v; h->splat_radius_d = (double)v; break;
+        case FLUID_ASPECT: h->cfg.aspect = v; h->aspect_d = (double)v; break;
         case FLUID_JACOBI_BLOCK: h->cfg.jacobi_block = (int)(v + 0.5f); break;
         default: return fail(h, FLUID_ERR_INVALID, "unknown param key %d", key);
     }
+    return FLUID_OK;
+}
+
+// The JS config values are doubles; two of them enter double arithmetic on the host before the
+// single narrowing of gl.uniform1f (correctRadius S:1457-1462: SPLAT_RADIUS / 100 * aspectRatio),
+// so a host mirror passes them at full precision.  Every other key narrows like fluid_set_param.
+int fluid_set_param_f64(fluid_t* h, int key, double v) {
+    if (!h) return FLUID_ERR_INVALID;
+    int rc = fluid_set_param(h, key, (float)v);
+    if (rc) return rc;
+    if (key == FLUID_SPLAT_RADIUS) h->splat_radius_d = v;
+    if (key == FLUID_ASPECT) h->aspect_d = v;
     return FLUID_OK;
 }
 
@@ -621,10 +662,10 @@ static int do_curl(fluid_t* h, Grid g) {
     curl_kernel<<<grid2d(g.W, g.j_hi - g.j_lo, b), b, 0, h->stream>>>((const float2*)h->velocity.read, h->curl, g);
     return check_launch(h, "curl_kernel");
 }
-static int do_vorticity(fluid_t* h, Grid g, float dt) {
+static int do_vorticity(fluid_t* h, Grid g) {
     dim3 b(64, 4);
     vorticity_kernel<<<grid2d(g.W, g.j_hi - g.j_lo, b), b, 0, h->stream>>>(
-        (const float2*)h->velocity.read, h->curl, (float2*)h->velocity.write, g, h->cfg.curl, dt);
+        (const float2*)h->velocity.read, h->curl, (float2*)h->velocity.write, g, h->cfg.curl, h->dt_dev);
     int rc = check_launch(h, "vorticity_kernel"); if (rc) return rc;
     swap_v(h);                                   // S:1246
     return FLUID_OK;
@@ -635,12 +676,12 @@ static int do_divergence(fluid_t* h, Grid g) {
         (const float2*)h->velocity.read, h->divergence, g);
     return check_launch(h, "divergence_kernel");
 }
-static int do_cvd(fluid_t* h, Grid g, float dt) {
+static int do_cvd(fluid_t* h, Grid g) {
     dim3 b(64, 4);
     dim3 grid((g.W + CVD_TX - 1) / CVD_TX, (g.j_hi - g.j_lo + CVD_TY - 1) / CVD_TY);
     curl_vorticity_divergence_kernel<<<grid, b, 0, h->stream>>>(
         (const float2*)h->velocity.read, h->curl, (float2*)h->velocity.write, h->divergence, g,
-        h->cfg.curl, dt);
+        h->cfg.curl, h->dt_dev);
     int rc = check_launch(h, "curl_vorticity_divergence_kernel"); if (rc) return rc;
     swap_v(h);
     return FLUID_OK;
@@ -657,13 +698,13 @@ static int do_gradient(fluid_t* h, Grid g) {
 static void valid_rows(int r0, int r1, int g, int H, int* lo, int* hi) {
     *lo = std::max(r0 - g, 0); *hi = std::min(r1 + g, H);
 }
-static int do_advect_velocity(fluid_t* h, Grid out, float dt) {
+static int do_advect_velocity(fluid_t* h, Grid out) {
     dim3 b(64, 4);
     AdvectArgs a{};
     a.vel = sim_grid(h); a.src = out;
     valid_rows(h->row0, h->row1, h->G, h->cfg.sim_h, &a.vel_lo, &a.vel_hi);
     a.src_lo = a.vel_lo; a.src_hi = a.vel_hi;
-    a.dt = dt; a.dissipation = h->cfg.velocity_dissipation; a.halo_violation = h->halo_flag;
+    a.dtp = h->dt_dev; a.dissipation = h->cfg.velocity_dissipation; a.halo_violation = h->halo_flag;
     const bool p2 = is_pow2(h->cfg.sim_w) && is_pow2(h->cfg.sim_h);
     if (p2) advect_velocity_kernel<true><<<grid2d(out.W, out.j_hi - out.j_lo, b), b, 0, h->stream>>>(
         (const float2*)h->velocity.read, (float2*)h->velocity.write, a);
@@ -673,14 +714,14 @@ static int do_advect_velocity(fluid_t* h, Grid out, float dt) {
     swap_v(h);                                   // S:1285
     return FLUID_OK;
 }
-static int do_advect_dye(fluid_t* h, float dt) {
+static int do_advect_dye(fluid_t* h) {
     dim3 b(64, 4);
     AdvectArgs a{};
     a.vel = sim_grid(h); a.src = dye_grid(h);
     // after the velocity advection the slab holds valid velocity on owned rows +- 3
     valid_rows(h->row0, h->row1, h->slab() ? 3 : 0, h->cfg.sim_h, &a.vel_lo, &a.vel_hi);
     valid_rows(h->drow0, h->drow1, h->Gd, h->cfg.dye_h, &a.src_lo, &a.src_hi);
-    a.dt = dt; a.dissipation = h->cfg.density_dissipation; a.halo_violation = h->halo_flag;
+    a.dtp = h->dt_dev; a.dissipation = h->cfg.density_dissipation; a.halo_violation = h->halo_flag;
     const bool p2 = is_pow2(h->cfg.sim_w) && is_pow2(h->cfg.sim_h) && is_pow2(h->cfg.dye_w) && is_pow2(h->cfg.dye_h);
     const bool same = h->cfg.sim_w == h->cfg.dye_w && h->cfg.sim_h == h->cfg.dye_h;
     const dim3 gr = grid2d(a.src.W, a.src.j_hi - a.src.j_lo, b);
@@ -701,7 +742,8 @@ int fluid_pass_curl(fluid_t* h) {
 int fluid_pass_vorticity(fluid_t* h, float dt) {
     if (!h) return FLUID_ERR_INVALID;
     if (h->slab()) return not_on_slab(h, "fluid_pass_vorticity");
-    return do_vorticity(h, sim_grid(h), dt);
+    int rc = set_dt(h, dt); if (rc) return rc;
+    return do_vorticity(h, sim_grid(h));
 }
 int fluid_pass_divergence(fluid_t* h) {
     if (!h) return FLUID_ERR_INVALID;
@@ -711,7 +753,8 @@ int fluid_pass_divergence(fluid_t* h) {
 int fluid_pass_curl_vorticity_divergence(fluid_t* h, float dt) {
     if (!h) return FLUID_ERR_INVALID;
     if (h->slab()) return not_on_slab(h, "fluid_pass_curl_vorticity_divergence");
-    return do_cvd(h, sim_grid(h), dt);
+    int rc = set_dt(h, dt); if (rc) return rc;
+    return do_cvd(h, sim_grid(h));
 }
 int fluid_pass_clear_pressure(fluid_t* h) {
     if (!h) return FLUID_ERR_INVALID;
@@ -734,12 +777,14 @@ int fluid_pass_gradient_subtract(fluid_t* h) {
 int fluid_pass_advect_velocity(fluid_t* h, float dt) {
     if (!h) return FLUID_ERR_INVALID;
     if (h->slab()) return not_on_slab(h, "fluid_pass_advect_velocity");
-    return do_advect_velocity(h, sim_grid(h), dt);
+    int rc = set_dt(h, dt); if (rc) return rc;
+    return do_advect_velocity(h, sim_grid(h));
 }
 int fluid_pass_advect_dye(fluid_t* h, float dt) {
     if (!h) return FLUID_ERR_INVALID;
     if (h->slab()) return not_on_slab(h, "fluid_pass_advect_dye");
-    return do_advect_dye(h, dt);
+    int rc = set_dt(h, dt); if (rc) return rc;
+    return do_advect_dye(h);
 }
 
 // step(dt), S:1231-1294.
@@ -747,7 +792,7 @@ int fluid_pass_advect_dye(fluid_t* h, float dt) {
 // halos below; curl / vorticity / divergence / gradientSubtract read ghost rows that the previous
 // step's advection (velocity on owned rows +- 3) and the last Jacobi launch (pressure on owned
 // rows +- 1) already computed redundantly.
-static int step_enqueue(fluid_t* h, float dt, bool timed) {
+static int step_enqueue(fluid_t* h, bool timed) {
     const uint64_t l0 = h->launches;
     const int W = h->cfg.sim_w;
     int rc;
@@ -759,10 +804,10 @@ static int step_enqueue(fluid_t* h, float dt, bool timed) {
     }
     if (h->cfg.flags & FLUID_FLAG_UNFUSED) {
         if ((rc = do_curl(h, sim_grid_ext(h, h->slab() ? 2 : 0)))) return rc;
-        if ((rc = do_vorticity(h, sim_grid_ext(h, h->slab() ? 1 : 0), dt))) return rc;
+        if ((rc = do_vorticity(h, sim_grid_ext(h, h->slab() ? 1 : 0)))) return rc;
         if ((rc = do_divergence(h, sim_grid(h)))) return rc;
     } else {
-        if ((rc = do_cvd(h, sim_grid(h), dt))) return rc;
+        if ((rc = do_cvd(h, sim_grid(h)))) return rc;
     }
     if (timed) cudaEventRecord(h->tev[1], h->stream);
     if ((rc = run_jacobi(h, h->cfg.pressure_iterations, true, &jl))) return rc;
@@ -772,12 +817,12 @@ static int step_enqueue(fluid_t* h, float dt, bool timed) {
     if (h->slab()) {   // advection halo #1: G rows of the projected velocity
         if ((rc = exchange_rows(h, HB_VELOCITY, h->velocity.read, (size_t)W * sizeof(float2), h->roff, h->row0, h->row1, h->G))) return rc;
     }
-    if ((rc = do_advect_velocity(h, sim_grid_ext(h, h->slab() ? 3 : 0), dt))) return rc;
+    if ((rc = do_advect_velocity(h, sim_grid_ext(h, h->slab() ? 3 : 0)))) return rc;
     if (timed) cudaEventRecord(h->tev[4], h->stream);
     if (h->slab()) {   // advection halo #2: Gd rows of dye
         if ((rc = exchange_rows(h, HB_DYE, h->dye.read, (size_t)h->cfg.dye_w * sizeof(float4), h->droff, h->drow0, h->drow1, h->Gd))) return rc;
     }
-    if ((rc = do_advect_dye(h, dt))) return rc;
+    if ((rc = do_advect_dye(h))) return rc;
     if (timed) cudaEventRecord(h->tev[5], h->stream);
     h->timing.jacobi_launches = jl;
     h->timing.total_launches = (int)(h->launches - l0);
@@ -788,26 +833,28 @@ static int step_enqueue(fluid_t* h, float dt, bool timed) {
 // The reference pays one draw call per pass (7 + PRESSURE_ITERATIONS per step) and is bound by
 // that at its default 128^2 grid.  Here a step is 4 + ceil(iters/10) kernels, and on a single GPU
 // they are replayed as ONE instantiated CUDA graph.  A graph bakes in kernel arguments, so the
-// cache key holds everything they depend on: dt, the config scalars, the grid sizes and which
-// half of each ping-pong pair is currently `.read`.
+// cache key holds everything they depend on: the config scalars, the grid sizes and which half of
+// each ping-pong pair is currently `.read`.  dt is NOT part of the key: kernels read it from
+// device memory (set_dt), so the reference's frame loop — calcDeltaTime() yields a different dt
+// on every frame (S:1188-1194) — replays the same two graphs (one per ping-pong parity).
 int fluid_step(fluid_t* h, float dt) {
     if (!h) return FLUID_ERR_INVALID;
     const bool no_graph = (h->cfg.flags & FLUID_FLAG_NO_GRAPH) != 0;
-    if (no_graph || h->slab()) return step_enqueue(h, dt, no_graph);
+    { int rc = set_dt(h, dt); if (rc) return rc; }
+    if (no_graph || h->slab()) return step_enqueue(h, no_graph);
     char key[256];
     const fluid_config& c = h->cfg;
-    unsigned dtb; memcpy(&dtb, &dt, sizeof dtb);
-    snprintf(key, sizeof key, "%08x|%a|%a|%a|%a|%d|%d|%u|%d%d%d|%dx%d|%dx%d", dtb,
+    snprintf(key, sizeof key, "%a|%a|%a|%a|%d|%d|%u|%d%d%d|%dx%d|%dx%d",
              c.curl, c.pressure, c.velocity_dissipation, c.density_dissipation, c.pressure_iterations, c.jacobi_block,
              c.flags, h->par_v, h->par_p, h->par_dye, c.sim_w, c.sim_h, c.dye_w, c.dye_h);
     auto it = h->graphs.find(key);
     if (it == h->graphs.end()) {
-        if (h->graphs.size() > 64) drop_graphs(h);          // dt that never repeats: do not grow without bound
+        if (h->graphs.size() > 64) drop_graphs(h);          // config sliders dragged for a long time: stay bounded
         const int pv = h->par_v, pp = h->par_p, pd = h->par_dye;
-        const uint64_t l0 = h->launches;
+        const uint64_t l0 = h->launches, j0 = h->jacobi_kernel_launches;
         cudaGraph_t g = nullptr;
         CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-        int rc = step_enqueue(h, dt, false);
+        int rc = step_enqueue(h, false);
         cudaError_t e = cudaStreamEndCapture(h->stream, &g);
         if (rc) { if (g) cudaGraphDestroy(g); return rc; }
         if (e != cudaSuccess) return fail(h, FLUID_ERR_CUDA, "stream capture of step() failed: %s", cudaGetErrorString(e));
@@ -816,8 +863,8 @@ int fluid_step(fluid_t* h, float dt) {
         cudaGraphDestroy(g);
         if (e != cudaSuccess) return fail(h, FLUID_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
         sg.flip_v = pv ^ h->par_v; sg.flip_p = pp ^ h->par_p; sg.flip_dye = pd ^ h->par_dye;
-        sg.kernels = (int)(h->launches - l0); sg.jacobi_launches = h->timing.jacobi_launches;
-        h->launches = l0;                                    // captured, not yet executed
+        sg.kernels = (int)(h->launches - l0); sg.jacobi_launches = (int)(h->jacobi_kernel_launches - j0);
+        h->launches = l0; h->jacobi_kernel_launches = j0;    // captured, not yet executed
         ++h->graph_captures;
         it = h->graphs.emplace(key, sg).first;
         // the capture already performed the host-side swaps of this step
@@ -829,6 +876,7 @@ int fluid_step(fluid_t* h, float dt) {
     }
     CU(cudaGraphLaunch(it->second.exec, h->stream));
     h->launches += it->second.kernels;
+    h->jacobi_kernel_launches += it->second.jacobi_launches;
     h->timing.jacobi_launches = it->second.jacobi_launches;
     h->timing.total_launches = it->second.kernels;
     h->have_timing = false;
@@ -840,8 +888,8 @@ int fluid_step(fluid_t* h, float dt) {
 int fluid_splat(fluid_t* h, float x, float y, float dx, float dy, float r, float g, float b) {
     if (!h) return FLUID_ERR_INVALID;
     // correctRadius(config.SPLAT_RADIUS / 100.0): JS double arithmetic, narrowed by gl.uniform1f
-    double rad = (double)h->cfg.splat_radius / 100.0;
-    if (h->cfg.aspect > 1.0f) rad *= (double)h->cfg.aspect;
+    double rad = h->splat_radius_d / 100.0;
+    if (h->aspect_d > 1.0) rad *= h->aspect_d;
     const float radius = (float)rad;
     dim3 bl(64, 4);
     // a splat is point-wise, so the +-3 velocity ghost rows are simply splatted as well
@@ -1015,6 +1063,20 @@ int fluid_elapsed_ms(fluid_t* h, float* ms) {
 }
 
 uint64_t fluid_launch_count(fluid_t* h) { return h ? h->launches : 0; }
+
+uint64_t fluid_stat(fluid_t* h, int key) {
+    if (!h) return 0;
+    switch (key) {
+        case FLUID_STAT_LAUNCHES: return h->launches;
+        case FLUID_STAT_JACOBI_LAUNCHES: return h->jacobi_kernel_launches;
+        case FLUID_STAT_HALO_LAUNCHES: return h->halo_kernel_launches;
+        case FLUID_STAT_HALO_EXCHANGES: return h->halo_groups;
+        case FLUID_STAT_GRAPH_CAPTURES: return h->graph_captures;
+        case FLUID_STAT_GRAPH_LAUNCHES: return h->graph_launches;
+        case FLUID_STAT_HALO_TRANSPORT_P2P: return h->p2p ? 1 : 0;
+    }
+    return 0;
+}
 
 void* fluid_device_ptr(fluid_t* h, int field) {
     void* p; int w, rows, ch;

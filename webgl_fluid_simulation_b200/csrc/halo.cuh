@@ -136,6 +136,7 @@ int exchange_p2p(fluid_t* h, const HaloItem* it, int count) {
     int rc = check_launch(h, "halo_push_kernel"); if (rc) return rc;
     halo_wait_kernel<<<1, 1, 0, h->stream>>>(pa.my_flags, pa.present[0], pa.present[1], pa.seq, pa.err, pa.dbg);
     rc = check_launch(h, "halo_wait_kernel"); if (rc) return rc;
+    h->halo_kernel_launches += 2;
     ++h->halo_groups;
     return FLUID_OK;
 }

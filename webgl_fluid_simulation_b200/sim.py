@@ -22,7 +22,7 @@ import time
 import numpy as np
 
 from . import _lib
-from ._lib import FIELD, PARAM, Config, FluidError, Timing
+from ._lib import FIELD, PARAM, STAT, Config, FluidError, Timing
 
 
 def default_config() -> dict:
@@ -160,7 +160,9 @@ class FluidSimulation:
         }
         for k, v in vals.items():
             if self._pushed.get(k) != v:
-                self._check(self._L.fluid_set_param(self._h, PARAM[k], float(v)))
+                # JS numbers are doubles: SPLAT_RADIUS and the aspect enter double arithmetic in
+                # correctRadius (S:1457-1462) before the single fp32 narrowing of gl.uniform1f
+                self._check(self._L.fluid_set_param_f64(self._h, PARAM[k], float(v)))
                 self._pushed[k] = v
 
     def _dims(self, name):
@@ -313,11 +315,17 @@ class FluidSimulation:
         return delta / a if a > 1 else delta
 
     # ---- data access (the reference hands textures to GL; a host mirror hands arrays) ----------------
-    def readField(self, name) -> np.ndarray:
+    def readField(self, name, out: np.ndarray | None = None) -> np.ndarray:
         """framebufferToTexture (S:301-307) generalised: rows x width [x channels] float32, row 0 =
-        bottom.  On a slab rank: the rows this rank owns."""
+        bottom.  On a slab rank: the rows this rank owns.  `out`: a caller-owned float32 buffer of
+        the right size (e.g. pinned host memory) to read into instead of allocating."""
         w, h, c, _ = self._dims(name)
-        out = np.empty((h, w, c) if c > 1 else (h, w), np.float32)
+        shape = (h, w, c) if c > 1 else (h, w)
+        if out is None:
+            out = np.empty(shape, np.float32)
+        else:
+            assert out.dtype == np.float32 and out.flags.c_contiguous and out.size == h * w * c
+            out = out.reshape(shape)
         self._check(self._L.fluid_read(self._h, FIELD[name], out.ctypes.data_as(C.c_void_p), out.size))
         return out
 
@@ -377,6 +385,11 @@ class FluidSimulation:
 
     def launch_count(self) -> int:
         return int(self._L.fluid_launch_count(self._h))
+
+    def stat(self, name) -> int:
+        """Library counters (fluid_stat): launches, jacobi_launches, halo_launches, halo_exchanges,
+        graph_captures, graph_launches, halo_transport_p2p."""
+        return int(self._L.fluid_stat(self._h, STAT[name]))
 
     def device_ptr(self, name) -> int:
         return int(self._L.fluid_device_ptr(self._h, FIELD[name]) or 0)
