@@ -73,6 +73,9 @@ typedef enum fluid_param {
 #define FLUID_FLAG_UNFUSED   0x1u /* run curl / vorticity / divergence as 3 separate passes      */
 #define FLUID_FLAG_NO_GRAPH  0x2u /* launch step() pass by pass instead of as one CUDA graph     */
 #define FLUID_FLAG_NAIVE_JACOBI 0x4u /* one Jacobi sweep per launch (the literal S:1262 loop)    */
+#define FLUID_FLAG_TILED_PASSES 0x8u /* generation-1 kernels (one thread per fragment / smem tile) for
+                                        curl-vorticity-divergence and gradientSubtract instead of the
+                                        row-streaming ones (comparison + fallback path)              */
 
 typedef struct fluid_config {
     int32_t sim_w, sim_h;           /* getResolution(SIM_RESOLUTION)  S:983, S:1612-1624 */

@@ -264,6 +264,58 @@ def test_update_loop_with_jittered_dt_replays_two_graphs(pkg):
         s.close()
 
 
+@pytest.mark.parametrize("case", ["all_subnormal", "tiny_div_patch", "tiny_div_everywhere", "zeros_and_tiny"])
+def test_blocked_jacobi_bitwise_with_subnormal_and_tiny_values(pkg, oracle, case):
+    """The contracted tail fma(S, 0.25, -0.25 d) is exact only for d == 0 or |d| >= 2^-123
+    (tests/test_fma_contraction_cpu.py); cells of divergence below that are flagged in the
+    tiny-value map and their warps run the un-contracted form.  Fields full of subnormals, a patch
+    of tiny divergence inside ordinary data, and exact zeros must all stay bit-identical to the
+    oracle (which runs without flush-to-zero)."""
+    O = oracle
+    W, H, iters = 512, 200, 30
+    rng = np.random.default_rng(5)
+    p = rng.standard_normal((H, W)).astype(np.float32)
+    d = rng.uniform(-1, 1, (H, W)).astype(np.float32)
+    tiny = (rng.integers(1, 2 ** 23, (H, W)) * 2.0 ** -149).astype(np.float32) * rng.choice([-1, 1], (H, W)).astype(np.float32)
+    if case == "all_subnormal":
+        p = (tiny * 3).astype(np.float32); d = tiny.copy()
+    elif case == "tiny_div_patch":
+        d[60:90, 100:300] = tiny[60:90, 100:300]; p[55:95, 90:310] *= np.float32(2.0 ** -125)
+    elif case == "tiny_div_everywhere":
+        d = tiny.copy(); p *= np.float32(2.0 ** -124)
+    else:
+        d[:] = 0; d[::7, ::5] = tiny[::7, ::5]; p[:, : W // 2] = 0; p[:, W // 2:] *= np.float32(2.0 ** -126)
+    for jb in (0, 7):
+        s = make(pkg, W, H, 8, 8, jb=jb, PRESSURE_ITERATIONS=iters)
+        s.writeField("pressure", p); s.writeField("divergence", d)
+        s.pass_("pressure_solve")
+        got = s.readField("pressure"); s.close()
+        assert bits_equal(got, O.jacobi(O.clear(p, 0.8), d, iters)), (case, jb)
+
+
+def test_whole_step_bitwise_with_splat_far_field_subnormals(pkg, oracle):
+    """A Gaussian splat's far field underflows gradually (exp(-r^2/0.0025) passes through the
+    subnormal range), so real velocity / divergence fields DO contain tiny values: the fused
+    curl-vorticity-divergence pass must flag them for the Jacobi kernel.  Fields are written (the
+    same bits on both sides), then two whole steps must be bit-identical to the oracle."""
+    O = oracle
+    W = H = 256
+    z = np.zeros((H, W, 2), np.float32)
+    v = O.splat(z, 1.0, 0.3, 0.4, (400.0, -300.0, 0.0), O.correct_radius(0.25, 1.0))
+    v = O.splat(v, 1.0, 0.8, 0.7, (-250.0, 120.0, 0.0), O.correct_radius(0.25, 1.0))
+    assert ((np.abs(v) > 0) & (np.abs(v) < 2.0 ** -123)).any()          # the premise
+    dye = np.zeros((H, W, 4), np.float32); dye[..., 3] = 1
+    s = make(pkg, W, H, W, H)
+    ref = O.OracleSim(W, H, W, H)
+    s.writeField("velocity", v); s.writeField("dye", dye)
+    ref.velocity, ref.dye = v.copy(), dye.copy()
+    for _ in range(2):
+        s.step(DT); ref.step(DT)
+    for n in ("velocity", "pressure", "divergence", "curl"):
+        assert bits_equal(s.readField(n), getattr(ref, n)), n
+    s.close()
+
+
 def test_host_pressure_solve_matches_resident_path(pkg):
     W = H = 512
     rng = np.random.default_rng(1)

@@ -7,7 +7,9 @@
 #include <cstdlib>
 
 typedef unsigned long long u64;
-#define NCH 8           // independent dependency chains per thread
+#ifndef NCH
+#define NCH 8           // independent dependency chains per thread (compile with -DNCH=1 for dependent-issue latency)
+#endif
 #define BODY 4          // chain updates per loop iteration (per chain)
 
 enum Kind { K_FADD, K_FADD2, K_FFMA, K_FFMA2, K_FMUL2, K_MIX_1A2P, K_SHFL, K_FADD2_MOV, K_FADD_IMM, K_FFMA_IMM, K_NKIND };

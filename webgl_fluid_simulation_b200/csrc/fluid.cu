@@ -5,6 +5,7 @@
 // every entry point either launches CUDA kernels on the handle's stream or fails.
 #include "../../include/fluid.h"
 
+#include <cuda.h>            // CUtensorMap types only: the encoder is fetched through cudaGetDriverEntryPoint
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -19,6 +20,7 @@
 #include "jacobi.cuh"
 #include "nccl_dl.h"
 #include "passes.cuh"
+#include "stream_passes.cuh"
 
 namespace {
 
@@ -47,12 +49,17 @@ struct fluid {
     uint64_t jacobi_kernel_launches = 0;   // Jacobi kernels only (fluid_stat FLUID_STAT_JACOBI_LAUNCHES)
     uint64_t halo_kernel_launches = 0;     // halo_push / halo_wait kernels of the peer-memory transport
     float* dt_dev = nullptr;               // step()'s dt lives in device memory: one graph serves every dt
+    unsigned char* tiny_map = nullptr;     // where divergence has 0 < |d| < 2^-123 (jacobi.cuh): 1 byte per 128x32 cells, GLOBAL rows
+    size_t tiny_map_bytes = 0;
+    // 2-D tensor maps (TMA staging of the blocked Jacobi kernel) of the two pressure buffers and divergence
+    struct Tmaps { CUtensorMap p[2]; void* p_ptr[2] = {nullptr, nullptr}; CUtensorMap d; bool ok = false; } tmaps;
     double splat_radius_d = 0.25;          // config.SPLAT_RADIUS and the canvas aspect as the JS doubles they are
     double aspect_d = 1.0;                 // (correctRadius S:1457-1462 is double arithmetic, narrowed once)
     fluid_timing timing{};
     bool have_timing = false;
     std::string err;
     int jacobi_rows_override = 0;    // FLUID_JACOBI_ROWS env (tuning)
+    int jacobi_warps_per_sm = 0;     // FLUID_JACOBI_WARPS env (tuning): cap on resident streams per SM used to size the chunks
 
     // ---- row-slab decomposition.  Single GPU: rank 0 of 1, no ghost rows. -------------
     int rank = 0, world = 1;
@@ -157,21 +164,92 @@ int set_dt(fluid_t* h, float dt) {
 
 #include "halo.cuh"
 
+// ---- the tiny-divergence map (jacobi.cuh): one byte per 128 x 32 cells of the GLOBAL grid -------------
+int alloc_tiny_map(fluid_t* h) {
+    cudaFree(h->tiny_map); h->tiny_map = nullptr;
+    h->tiny_map_bytes = (size_t)tiny_map_w(h->cfg.sim_w) * tiny_map_h(h->cfg.sim_h);
+    CU(cudaMalloc((void**)&h->tiny_map, h->tiny_map_bytes));
+    CU(cudaMemsetAsync(h->tiny_map, 0, h->tiny_map_bytes, h->stream));
+    return FLUID_OK;
+}
+// before a pass that recomputes divergence everywhere (the pass then flags cells itself)
+int clear_tiny_map(fluid_t* h) {
+    CU(cudaMemsetAsync(h->tiny_map, 0, h->tiny_map_bytes, h->stream));
+    return FLUID_OK;
+}
+// divergence rows [j_lo, j_hi) came from outside (host write, neighbour rank): flag their cells
+int scan_tiny(fluid_t* h, int j_lo, int j_hi) {
+    if (j_hi <= j_lo) return FLUID_OK;
+    dim3 b(256), g((h->cfg.sim_w + 255) / 256, j_hi - j_lo);
+    tiny_scan_kernel<<<g, b, 0, h->stream>>>(h->divergence, h->tiny_map, h->cfg.sim_w, h->roff, j_lo, j_hi);
+    return check_launch(h, "tiny_scan_kernel");
+}
+
 // ---- Jacobi dispatch -----------------------------------------------------------------------------
 
 constexpr int KMAX = 12;
+
+// cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess) { cudaGetLastError(); return nullptr; }
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+// fp32 field of `rows` x W as a 2-D tensor; box = 128 columns x 3 rows, no swizzle, out-of-range
+// elements read as zero (the blocked kernel never lets them reach a valid output)
+bool encode_rows_map(CUtensorMap* tm, void* base, int W, int rows) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc || W % 4 != 0) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)W, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)W * sizeof(float)};
+    const cuuint32_t box[2] = {128, 3};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// (re)build the tensor maps after the pressure / divergence buffers were allocated
+void build_tmaps(fluid_t* h) {
+    h->tmaps.ok = false;
+    if (h->cfg.sim_w % 4 != 0 || h->cfg.sim_w < 16) return;
+    const int rows = h->lrows();
+    h->tmaps.p_ptr[0] = h->pressure.read; h->tmaps.p_ptr[1] = h->pressure.write;
+    h->tmaps.ok = encode_rows_map(&h->tmaps.p[0], h->pressure.read, h->cfg.sim_w, rows) &&
+                  encode_rows_map(&h->tmaps.p[1], h->pressure.write, h->cfg.sim_w, rows) &&
+                  encode_rows_map(&h->tmaps.d, h->divergence, h->cfg.sim_w, rows);
+}
+
+// staging of the blocked kernel: 2-D TMA boxes when tensor maps could be built (FLUID_TB_STAGE=ldgsts
+// selects the per-lane cp.async ring instead)
+bool tb_use_tma(const fluid_t* h) {
+    static const bool want_ldgsts = getenv("FLUID_TB_STAGE") && !strcmp(getenv("FLUID_TB_STAGE"), "ldgsts");
+    return h->tmaps.ok && !want_ldgsts;
+}
 
 template <int K, bool SCALE>
 int launch_tb(fluid_t* h, const JacobiArgs& a) {
     using T = TB<K>;
     const int nxw = (a.W + T::VALID - 1) / T::VALID;
     const int nch = (a.out_hi - a.out_lo + a.rows_per_chunk - 1) / a.rows_per_chunk;
-    // staging fill: per-lane LDGSTS (default) or TMA bulk copies (FLUID_TB_STAGE=tma).  Measured on
-    // B200 at 4096^2 x 50: LDGSTS 0.287 ms, TMA 0.330 ms — a 512 B row segment per warp is too small
-    // for the elected-lane + mbarrier handshake to pay (profiles/r01_tma_vs_ldgsts.txt).
-    static const bool tma = getenv("FLUID_TB_STAGE") && !strcmp(getenv("FLUID_TB_STAGE"), "tma");
-    if (tma) jacobi_tb_kernel<K, SCALE, true><<<nxw * nch, 32, T::SMEM, h->stream>>>(a);   // one warp per CTA
-    else jacobi_tb_kernel<K, SCALE, false><<<nxw * nch, 32, T::SMEM, h->stream>>>(a);
+    TmapPair maps;
+    memset(&maps, 0, sizeof maps);
+    if (tb_use_tma(h)) {
+        const int k = (a.pin == h->tmaps.p_ptr[0]) ? 0 : 1;
+        memcpy(maps.p, &h->tmaps.p[k], sizeof(CUtensorMap));
+        memcpy(maps.d, &h->tmaps.d, sizeof(CUtensorMap));
+        jacobi_tb_kernel<K, SCALE, true><<<nxw * nch, 32, T::SMEM_TMA, h->stream>>>(a, maps);   // one warp per CTA
+    } else {
+        jacobi_tb_kernel<K, SCALE, false><<<nxw * nch, 32, T::SMEM_LDGSTS, h->stream>>>(a, maps);
+    }
     ++h->jacobi_kernel_launches;
     return check_launch(h, "jacobi_tb_kernel");
 }
@@ -189,8 +267,10 @@ int tb_rows(const fluid_t* h, int W, int rows) {
     using T = TB<K>;
     const int nxw = (W + T::VALID - 1) / T::VALID;
     int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, jacobi_tb_kernel<K, false, true>, 32, T::SMEM);
+    if (tb_use_tma(h)) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, jacobi_tb_kernel<K, false, true>, 32, T::SMEM_TMA);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, jacobi_tb_kernel<K, false, false>, 32, T::SMEM_LDGSTS);
     if (occ < 1) occ = 1;
+    if (h->jacobi_warps_per_sm > 0) occ = std::min(occ, h->jacobi_warps_per_sm);
     const int resident_warps = h->sm_count * occ;
     const int nch = std::max(1, resident_warps / nxw);
     int r = (rows + nch - 1) / nch;
@@ -227,6 +307,7 @@ int run_jacobi(fluid_t* h, int iters, bool scale_first, int* launches_out) {
     a.div = h->divergence; a.W = W; a.H = H; a.row_off = h->roff; a.out_lo = h->row0; a.out_hi = h->row1;
     a.scale = h->cfg.pressure;
     a.err = h->halo_flag;
+    a.tiny_map = h->tiny_map;
     int kb = h->cfg.jacobi_block > 0 ? h->cfg.jacobi_block : 10;  // tuned on B200: profiles/r01_tune_jacobi.txt
     kb = std::min(kb, KMAX);
     if (h->slab()) kb = std::max(1, std::min(kb, h->G - 1));
@@ -256,10 +337,15 @@ int run_jacobi(fluid_t* h, int iters, bool scale_first, int* launches_out) {
             HaloItem it[2] = {{h->pressure.read, (size_t)W * sizeof(float), h->roff, h->row0, h->row1, iters + 1, HB_PRESSURE},
                               {h->divergence, (size_t)W * sizeof(float), h->roff, h->row0, h->row1, iters, HB_DIVERGENCE}};
             int rc = exchange_many(h, it, 2); if (rc) return rc;
+            // the neighbours' divergence rows: flag their tiny values like the local producers do
+            if ((rc = scan_tiny(h, std::max(h->row0 - iters, 0), h->row0))) return rc;
+            if ((rc = scan_tiny(h, h->row1, std::min(h->row1 + iters, H)))) return rc;
         } else {
             const int kmax = base + (extra ? 1 : 0);
             int rc = exchange_rows(h, HB_DIVERGENCE, h->divergence, (size_t)W * sizeof(float), h->roff, h->row0, h->row1, kmax);
             if (rc) return rc;
+            if ((rc = scan_tiny(h, std::max(h->row0 - kmax, 0), h->row0))) return rc;
+            if ((rc = scan_tiny(h, h->row1, std::min(h->row1 + kmax, H)))) return rc;
         }
     }
     int remaining = iters;
@@ -340,6 +426,8 @@ int alloc_fields(fluid_t* h) {
         CU(cudaMemsetAsync(h->divergence, 0, n * sizeof(float), h->stream));
         CU(cudaMemsetAsync(h->curl, 0, n * sizeof(float), h->stream));
     }
+    { int rc = alloc_tiny_map(h); if (rc) return rc; }
+    build_tmaps(h);
     fill_alpha_kernel<<<(unsigned)((nd + 255) / 256), 256, 0, h->stream>>>((float4*)h->dye.read, nd);
     fill_alpha_kernel<<<(unsigned)((nd + 255) / 256), 256, 0, h->stream>>>((float4*)h->dye.write, nd);
     return check_launch(h, "fill_alpha_kernel", 2);
@@ -357,6 +445,8 @@ void free_fields(fluid_t* h) {
     }
     h->velocity = Pair{}; h->dye = Pair{}; h->pressure = Pair{};
     h->divergence = h->curl = nullptr;
+    cudaFree(h->tiny_map); h->tiny_map = nullptr;
+    h->tmaps.ok = false;
 }
 
 // pointer to the first OWNED row of a field's .read buffer, plus its owned extent
@@ -446,6 +536,7 @@ int create_common(const fluid_config* cfg, int rank, int world, const void* uid,
     }
     h->roff = h->row0 - h->G; h->droff = h->drow0 - h->Gd;
     if (const char* e = getenv("FLUID_JACOBI_ROWS")) h->jacobi_rows_override = atoi(e);
+    if (const char* e = getenv("FLUID_JACOBI_WARPS")) h->jacobi_warps_per_sm = atoi(e);
     auto body = [&]() -> int {
         CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         for (auto& e : h->mark) CU(cudaEventCreate(&e));
@@ -672,21 +763,57 @@ static int do_vorticity(fluid_t* h, Grid g) {
 }
 static int do_divergence(fluid_t* h, Grid g) {
     dim3 b(64, 4);
+    { int rc = clear_tiny_map(h); if (rc) return rc; }
     divergence_kernel<<<grid2d(g.W, g.j_hi - g.j_lo, b), b, 0, h->stream>>>(
-        (const float2*)h->velocity.read, h->divergence, g);
+        (const float2*)h->velocity.read, h->divergence, g, h->tiny_map);
     return check_launch(h, "divergence_kernel");
 }
+// rows per warp stream of the row-streaming kernels: enough streams to fill the chip (~16 warps per
+// SM), at least `rmin` rows each so that the halo rows a stream re-reads stay a small fraction
+static StreamArgs stream_args(const fluid_t* h, Grid g, int cols_per_window, int rmin) {
+    StreamArgs a{};
+    a.g = g;
+    a.nxw = (g.W + cols_per_window - 1) / cols_per_window;
+    const int rows = g.j_hi - g.j_lo;
+    const int chunks = std::max(1, h->sm_count * 16 / a.nxw);
+    a.rows_per_chunk = std::min(std::max((rows + chunks - 1) / chunks, rmin), std::max(rows, 1));
+    return a;
+}
+static bool streaming_ok(const fluid_t* h) {
+    return h->cfg.sim_w % 4 == 0 && h->cfg.sim_w >= 8 && !(h->cfg.flags & FLUID_FLAG_TILED_PASSES);
+}
+
 static int do_cvd(fluid_t* h, Grid g) {
+    { int rc = clear_tiny_map(h); if (rc) return rc; }
+    if (streaming_ok(h)) {
+        const StreamArgs a = stream_args(h, g, CVD2_VALID, 32);
+        const int nwarps = a.nxw * ((g.j_hi - g.j_lo + a.rows_per_chunk - 1) / a.rows_per_chunk);
+        cvd_stream_kernel<<<(nwarps + CVD2_WARPS - 1) / CVD2_WARPS, 32 * CVD2_WARPS, CVD2_SMEM, h->stream>>>(
+            (const float2*)h->velocity.read, h->curl, (float2*)h->velocity.write, h->divergence, a, h->cfg.curl,
+            h->dt_dev, h->tiny_map);
+        int rc = check_launch(h, "cvd_stream_kernel"); if (rc) return rc;
+        swap_v(h);
+        return FLUID_OK;
+    }
     dim3 b(64, 4);
     dim3 grid((g.W + CVD_TX - 1) / CVD_TX, (g.j_hi - g.j_lo + CVD_TY - 1) / CVD_TY);
     curl_vorticity_divergence_kernel<<<grid, b, 0, h->stream>>>(
         (const float2*)h->velocity.read, h->curl, (float2*)h->velocity.write, h->divergence, g,
-        h->cfg.curl, h->dt_dev);
+        h->cfg.curl, h->dt_dev, h->tiny_map);
     int rc = check_launch(h, "curl_vorticity_divergence_kernel"); if (rc) return rc;
     swap_v(h);
     return FLUID_OK;
 }
 static int do_gradient(fluid_t* h, Grid g) {
+    if (streaming_ok(h)) {
+        const StreamArgs a = stream_args(h, g, 128, 16);
+        const int nwarps = a.nxw * ((g.j_hi - g.j_lo + a.rows_per_chunk - 1) / a.rows_per_chunk);
+        gradient_stream_kernel<<<(nwarps + GS_WARPS - 1) / GS_WARPS, 32 * GS_WARPS, 0, h->stream>>>(
+            (const float*)h->pressure.read, (const float2*)h->velocity.read, (float2*)h->velocity.write, a);
+        int rc = check_launch(h, "gradient_stream_kernel"); if (rc) return rc;
+        swap_v(h);                                   // S:1273
+        return FLUID_OK;
+    }
     dim3 b(64, 4);
     gradient_subtract_kernel<<<grid2d(g.W, g.j_hi - g.j_lo, b), b, 0, h->stream>>>(
         (const float*)h->pressure.read, (const float2*)h->velocity.read, (float2*)h->velocity.write, g);
@@ -705,6 +832,7 @@ static int do_advect_velocity(fluid_t* h, Grid out) {
     valid_rows(h->row0, h->row1, h->G, h->cfg.sim_h, &a.vel_lo, &a.vel_hi);
     a.src_lo = a.vel_lo; a.src_hi = a.vel_hi;
     a.dtp = h->dt_dev; a.dissipation = h->cfg.velocity_dissipation; a.halo_violation = h->halo_flag;
+    a.tsx = a.dsx = (float)(1.0 / (double)h->cfg.sim_w); a.tsy = a.dsy = (float)(1.0 / (double)h->cfg.sim_h);
     const bool p2 = is_pow2(h->cfg.sim_w) && is_pow2(h->cfg.sim_h);
     if (p2) advect_velocity_kernel<true><<<grid2d(out.W, out.j_hi - out.j_lo, b), b, 0, h->stream>>>(
         (const float2*)h->velocity.read, (float2*)h->velocity.write, a);
@@ -722,6 +850,8 @@ static int do_advect_dye(fluid_t* h) {
     valid_rows(h->row0, h->row1, h->slab() ? 3 : 0, h->cfg.sim_h, &a.vel_lo, &a.vel_hi);
     valid_rows(h->drow0, h->drow1, h->Gd, h->cfg.dye_h, &a.src_lo, &a.src_hi);
     a.dtp = h->dt_dev; a.dissipation = h->cfg.density_dissipation; a.halo_violation = h->halo_flag;
+    a.tsx = (float)(1.0 / (double)h->cfg.sim_w); a.tsy = (float)(1.0 / (double)h->cfg.sim_h);
+    a.dsx = (float)(1.0 / (double)h->cfg.dye_w); a.dsy = (float)(1.0 / (double)h->cfg.dye_h);
     const bool p2 = is_pow2(h->cfg.sim_w) && is_pow2(h->cfg.sim_h) && is_pow2(h->cfg.dye_w) && is_pow2(h->cfg.dye_h);
     const bool same = h->cfg.sim_w == h->cfg.dye_w && h->cfg.sim_h == h->cfg.dye_h;
     const dim3 gr = grid2d(a.src.W, a.src.j_hi - a.src.j_lo, b);
@@ -894,13 +1024,18 @@ int fluid_splat(fluid_t* h, float x, float y, float dx, float dy, float r, float
     dim3 bl(64, 4);
     // a splat is point-wise, so the +-3 velocity ghost rows are simply splatted as well
     Grid gs = sim_grid_ext(h, h->slab() ? 3 : 0), gd = dye_grid(h);
+    SplatArgs sa{};
+    sa.aspect = h->cfg.aspect; sa.px = x; sa.py = y; sa.radius = radius;
+    sa.g = gs; sa.pow2 = is_pow2(gs.W) && is_pow2(gs.H);
+    sa.tsx = (float)(1.0 / (double)gs.W); sa.tsy = (float)(1.0 / (double)gs.H);
     splat_velocity_kernel<<<grid2d(gs.W, gs.j_hi - gs.j_lo, bl), bl, 0, h->stream>>>(
-        (const float2*)h->velocity.read, (float2*)h->velocity.write, gs, h->cfg.aspect, x, y, dx, dy,
-        radius);
+        (const float2*)h->velocity.read, (float2*)h->velocity.write, sa, dx, dy);
     int rc = check_launch(h, "splat_velocity_kernel"); if (rc) return rc;
     swap_v(h);                                   // S:1449
+    sa.g = gd; sa.pow2 = is_pow2(gd.W) && is_pow2(gd.H);
+    sa.tsx = (float)(1.0 / (double)gd.W); sa.tsy = (float)(1.0 / (double)gd.H);
     splat_dye_kernel<<<grid2d(gd.W, gd.j_hi - gd.j_lo, bl), bl, 0, h->stream>>>(
-        (const float4*)h->dye.read, (float4*)h->dye.write, gd, h->cfg.aspect, x, y, r, g, b, radius);
+        (const float4*)h->dye.read, (float4*)h->dye.write, sa, r, g, b);
     rc = check_launch(h, "splat_dye_kernel"); if (rc) return rc;
     swap_dye(h);                                        // S:1454
     return FLUID_OK;
@@ -953,6 +1088,8 @@ int fluid_resize(fluid_t* h, int sim_w, int sim_h, int dye_w, int dye_h) {
     CU(cudaMemsetAsync(h->curl, 0, n * sizeof(float), h->stream));
     h->cfg.sim_w = sim_w; h->cfg.sim_h = sim_h; h->cfg.dye_w = dye_w; h->cfg.dye_h = dye_h;
     h->row0 = 0; h->row1 = sim_h; h->drow0 = 0; h->drow1 = dye_h; h->roff = 0; h->droff = 0;
+    { int rc = alloc_tiny_map(h); if (rc) return rc; }
+    build_tmaps(h);
     return FLUID_OK;
 }
 
@@ -990,6 +1127,10 @@ int fluid_write(fluid_t* h, int field, const float* host, size_t n_floats) {
     CU(cudaMemcpyAsync(p, host, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     if (field == FLUID_FIELD_VELOCITY) h->v_ghost_valid = false;   // ghosts rebuilt by the next step
+    if (field == FLUID_FIELD_DIVERGENCE) {                          // host-provided divergence: rebuild the map
+        int rc = clear_tiny_map(h); if (rc) return rc;
+        if ((rc = scan_tiny(h, h->row0, h->row1))) return rc;
+    }
     return FLUID_OK;
 }
 
@@ -1001,7 +1142,9 @@ int fluid_pressure_solve_host(fluid_t* h, const float* div_host, float* p_host, 
     // make the copies asynchronous DMA.  Either way all three copies are inside this call.
     CU(cudaMemcpyAsync(h->divergence + go, div_host, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync((float*)h->pressure.read + go, p_host, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-    int rc = run_jacobi(h, iters, true, nullptr); if (rc) return rc;
+    int rc = clear_tiny_map(h); if (rc) return rc;
+    if ((rc = scan_tiny(h, h->row0, h->row1))) return rc;
+    rc = run_jacobi(h, iters, true, nullptr); if (rc) return rc;
     CU(cudaMemcpyAsync(p_host, (float*)h->pressure.read + go, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return FLUID_OK;
@@ -1023,7 +1166,8 @@ int fluid_render(fluid_t* h, int width, int height, int shading, float back_r, f
     }
     dim3 b(32, 8);
     display_kernel<<<grid2d(width, height, b), b, 0, h->stream>>>((const float4*)h->dye.read, h->cfg.dye_w, h->cfg.dye_h,
-                                                                h->frame, width, height, shading, back_r, back_g, back_b);
+                                                                h->frame, width, height, shading, back_r, back_g, back_b,
+                                                                make_float2((float)(1.0 / (double)width), (float)(1.0 / (double)height)));
     int rc = check_launch(h, "display_kernel"); if (rc) return rc;
     CU(cudaMemcpyAsync(host_rgba, h->frame, cells * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));

@@ -43,6 +43,14 @@ struct JacobiArgs {
     int rows_per_chunk;  // tb kernel: output rows per warp stream
     float scale;         // SCALE: value of config.PRESSURE
     int* err;            // device error word (3 = a bounded mbarrier wait gave up)
+    const unsigned char* tiny_map;   // tb kernel: where divergence defeats the fma contraction (may be null)
+};
+
+// the two tensor maps a temporally blocked launch reads through (TMA staging); 64-byte aligned
+// CUtensorMap images, passed by value as a __grid_constant__ kernel parameter
+struct __align__(64) TmapPair {
+    unsigned char p[128];
+    unsigned char d[128];
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -102,15 +110,50 @@ __global__ void __launch_bounds__(256) jacobi_sweep_kernel(JacobiArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Temporally blocked kernel, generation 7.
+//
+// Arithmetic.  The fp32 pipes deliver 32 lane-operations per cycle per SM sub-partition whether
+// they are issued scalar (FADD/FFMA, 1 cycle) or packed (FADD2/FFMA2, 2 cycles) — measured,
+// tools/ubench/fp32_pipe.cu — so the kernel's floor is LANE-OPERATIONS per update, and the packed
+// forms only save issue slots.  The reference expression costs 5:  ((((L+R)+B)+T)-d)*0.25.  The
+// last two contract into ONE fma with a pre-scaled divergence,
+//        fma(S, 0.25, -0.25*d)  ==  (S - d) * 0.25      bit for bit,
+// whenever d == 0 or |d| >= 2^-123 (and the result does not overflow):  -0.25*d is then exact;
+// for |S-d| >= 2^-124 scaling by 2^-2 commutes with the rounding of S-d (normal results); for
+// |S-d| < 2^-124 <= |d|/2 Sterbenz makes S-d exact, so both sides round the same real number once.
+// A divergence value with 0 < |d| < 2^-123 (subnormal-range far fields of a Gaussian splat do
+// produce them) can double-round differently, so the producers of `divergence` keep a coarse map —
+// one byte per 128-column x 32-row cell — of where such values occur, and a warp whose footprint
+// touches a flagged cell runs the EXACT instantiation (subtract, then multiply).  4 lane-ops per
+// update instead of 5 everywhere else.
+//
+// Staging.  p / div rows reach a warp through a shared-memory ring, filled either
+//   * TMA: by 2-D tensor-map TMA (cp.async.bulk.tensor.2d, SASS UTMALDG): one elected lane arms an
+//     mbarrier and fetches a 128-column x 3-row box of p and of div per pipeline block; columns
+//     outside the grid and rows outside the buffer are zero-filled by the hardware (never used
+//     by a valid output); or
+//   * LDGSTS: by per-lane 16-byte cp.async (the generation-5 path, kept selectable).
 template <int K>
 struct TB {
     static constexpr int HX = (K + 3) / 4 * 4;       // x halo (columns) on each side of a window
     static constexpr int VALID = 128 - 2 * HX;       // columns a window produces
     static constexpr int RD = K + 3;                 // div register-ring slots
     static constexpr int U = 3;                      // pipeline steps per unrolled block
-    static constexpr int D = 8;                      // staging depth: rows in flight per stream
-    static constexpr int SMEM = D * 2 * 32 * (int)sizeof(float4) + D * 8;   // p + div staging rings + D mbarriers
+    // LDGSTS ring: D rows of p + D rows of div, one float4 per lane per row
+    static constexpr int D = 8;
+    static constexpr int SMEM_LDGSTS = D * 2 * 32 * (int)sizeof(float4);
+    // TMA ring: NS stages, each a 3-row box of p followed by a 3-row box of div (row = 512 B)
+    static constexpr int NS = 4;
+    static constexpr int STAGE4 = 2 * U * 32;        // float4 per stage
+    static constexpr int SMEM_TMA = NS * STAGE4 * (int)sizeof(float4) + NS * 8;
 };
+
+// coarse map of "divergence has a value with 0 < |d| < 2^-123 here": one byte per cell
+constexpr int TINY_CW = 128, TINY_CH = 32;
+constexpr float TINY_DIV = 9.4039548e-38f;           // 2^-123
+__host__ __device__ inline int tiny_map_w(int W) { return (W + TINY_CW - 1) / TINY_CW; }
+__host__ __device__ inline int tiny_map_h(int H) { return (H + TINY_CH - 1) / TINY_CH; }
+__device__ __forceinline__ bool is_tiny_div(float d) { return d != 0.0f && fabsf(d) < TINY_DIV; }
 
 // ---- cp.async (LDGSTS) staging: global -> shared without passing through registers ------------
 // Each lane copies, and later reads back, ONLY its own 16 bytes of a row, so the per-thread
@@ -122,11 +165,9 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-// ---- cp.async.bulk (1-D TMA, SASS UBLKCP) + mbarrier: the TMA variant of the same staging ring -----
-// One elected lane arms the slot's mbarrier with the byte count and issues two bulk copies (the p
-// and div row segments of this window, 512 B each away from the walls); the hardware completes the
-// barrier when the bytes have landed.  Waits are bounded: a mis-armed barrier costs an error word,
-// never a hung kernel.
+
+// ---- TMA (2-D tensor map) + mbarrier ----------------------------------------------------------------
+// Waits are bounded: a mis-armed barrier costs an error word, never a hung kernel.
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(void* bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -135,9 +176,9 @@ __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_expect_tx(void* bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, void* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, int x, int y, void* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(void* bar, unsigned parity) {
     unsigned ok;
@@ -146,7 +187,7 @@ __device__ __forceinline__ bool mbar_try_wait(void* bar, unsigned parity) {
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(void* bar, unsigned parity, int* err) {
-    if (mbar_try_wait(bar, parity)) return;              // the common case: the row landed long ago
+    if (mbar_try_wait(bar, parity)) return;              // the common case: the box landed long ago
 #pragma unroll 1
     for (int tries = 0; tries < (1 << 16); ++tries)      // each try_wait already blocks for a HW time slice
         if (mbar_try_wait(bar, parity)) return;
@@ -164,11 +205,9 @@ __device__ __forceinline__ float4 rev4(float4 v, bool rev) {
     return rev ? make_float4(v.w, v.z, v.y, v.x) : v;
 }
 
-// Blackwell packed fp32 arithmetic (FADD2 / FMUL2): two IEEE round-to-nearest results per issue
-// slot.  The kernel is issue-bound, so the vertical part of the stencil (+below, +above, -div,
-// *0.25 — element-wise on the (x,y) and (z,w) halves of a float4) is issued packed; the
-// horizontal sums need the misaligned pair (y,z) and stay scalar.  Rounding is per element and
-// identical to the scalar form, so results remain bit-identical to the reference expression.
+// Blackwell packed fp32 arithmetic (FADD2 / FMUL2 / FFMA2): two IEEE round-to-nearest results per
+// issue slot, element-wise on the (x,y) and (z,w) halves of a float4.  The horizontal sums need the
+// misaligned pair (y,z) and stay scalar.  Rounding is per element and identical to the scalar form.
 typedef unsigned long long u64;
 __device__ __forceinline__ u64 pack2(float a, float b) {
     u64 v; asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(a), "f"(b)); return v;
@@ -185,9 +224,14 @@ __device__ __forceinline__ u64 sub2(u64 a, u64 b) {
 __device__ __forceinline__ u64 mul2(u64 a, u64 b) {
     u64 c; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(c) : "l"(a), "l"(b)); return c;
 }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+    u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
+}
 
-// one Jacobi update of a float4 of row `c`, with rows below/above and the shuffled neighbours:
-//   o = ((((L + R) + below) + above) - d) * 0.25   per column, in that order
+// one Jacobi update of a float4 of row `c`, with rows below/above and the shuffled neighbours.
+//   EXACT:  o = ((((L + R) + below) + above) - d) * 0.25          (d = divergence)
+//   else :  o = fma(((L + R) + below) + above, 0.25, d)           (d = -0.25 * divergence)
+template <bool EXACT>
 __device__ __forceinline__ float4 jacobi4(const float4 below, const float4 c, const float4 above,
                                           const float4 d) {
     const float l = __shfl_up_sync(0xffffffffu, c.w, 1);
@@ -199,10 +243,15 @@ __device__ __forceinline__ float4 jacobi4(const float4 below, const float4 c, co
     hi = add2(hi, pack2(below.z, below.w));
     lo = add2(lo, pack2(above.x, above.y));
     hi = add2(hi, pack2(above.z, above.w));
-    lo = sub2(lo, pack2(d.x, d.y));
-    hi = sub2(hi, pack2(d.z, d.w));
-    lo = mul2(lo, q);
-    hi = mul2(hi, q);
+    if (EXACT) {
+        lo = sub2(lo, pack2(d.x, d.y));
+        hi = sub2(hi, pack2(d.z, d.w));
+        lo = mul2(lo, q);
+        hi = mul2(hi, q);
+    } else {
+        lo = fma2(lo, q, pack2(d.x, d.y));
+        hi = fma2(hi, q, pack2(d.z, d.w));
+    }
     float4 o;
     unpack2(lo, o.x, o.y);
     unpack2(hi, o.z, o.w);
@@ -211,25 +260,26 @@ __device__ __forceinline__ float4 jacobi4(const float4 below, const float4 c, co
 
 // Per-warp stream state that survives across unrolled blocks.
 struct TBStream {
+    float4* op;          // where level K's row of THIS step goes (advances one row per step)
+    int rout;            // global row index op points at  (= ys + s - K)
+    // LDGSTS variant
     const float4* pl;    // next p row to stage (this lane's float4 column group)
     const float4* dl;    // next div row to stage
-    float4* op;          // where level K's row of THIS step goes (advances one row per step)
-    float4* stage;       // this lane's cell of the staging slot consumed at this step
+    const float4* stage; // this lane's cell of the staging slot consumed at this step
     int rload;           // global row index pl/dl point at
-    int rout;            // global row index op points at  (= ys + s - K)
     int slot;            // staging slot consumed at this step (0..D-1)
-    // TMA variant only
-    unsigned phase;      // mbarrier parity of the slot consumed at this step
-    const float* pseg;   // next p row: first in-domain column of this window (warp-uniform)
-    const float* dseg;   // next div row, ditto
+    // TMA variant
+    int stg;             // stage consumed by this block (0..NS-1)
+    unsigned phase;      // mbarrier parity of that stage
+    int yfill;           // local row coordinate of the next box to fetch
 };
 
-struct TBSeg {           // the part of a window's 128 columns that lies inside the grid (TMA variant)
-    unsigned bytes;      // (ce - cs) * 4, a multiple of 16
-    int dst4;            // float4 index of column cs inside a slot ((cs - x0) / 4)
-    int W;               // row pitch in floats
-    unsigned long long* bars;   // D mbarriers
-    float4* slots;       // smem4 base (slot q of p at slots + q*32, of div at slots + (D+q)*32)
+struct TBTma {           // warp-uniform TMA bookkeeping
+    const void* tm_p;    // tensor map of the source pressure buffer
+    const void* tm_d;    // tensor map of divergence
+    unsigned long long* bars;   // NS mbarriers
+    float4* slots;       // stage q at slots + q * STAGE4
+    int x0;              // first (possibly negative) column of the window
     int lane;
     int* err;
 };
@@ -239,53 +289,47 @@ struct TBSeg {           // the part of a window's 128 columns that lies inside 
 //     addressed with compile-time constants and never moved;
 //   * div: level t needs div[r] when it produces row r, i.e. at K different steps.  The last K+3
 //     rows live in the register ring dr[]: the row staged at phase ph sits in dr[K+ph], level t
-//     reads dr[K+ph-t], and the ring is shifted down by 3 at the end of the block (4K MOVs per
-//     3 steps on the otherwise idle ALU pipe).  Earlier variants: a shared-memory ring made the
-//     LSU data pipe the bottleneck (LDS.128 = 4 wavefronts); a move-free ring unrolled RD times
-//     blew the instruction cache.
-//   * p / div rows arrive through a D-deep cp.async staging ring in shared memory: D rows in
-//     flight per stream give the memory-level parallelism the few resident warps cannot.
-// EDGE instantiates the wall selects in y, REV the mirrored-lane reversal in x; both are chosen
-// by warp-uniform branches OUTSIDE the steady-state loop.
-template <int K, bool SCALE, bool EDGE, bool REV, bool TMA>
+//     reads dr[K+ph-t], and the ring is shifted down by 3 at the end of the block (MOVs issue on
+//     the ALU pipe, beside the fp32 pipe that bounds the kernel);
+//   * EDGE instantiates the wall selects in y, REV the mirrored-lane reversal in x, EXACT the
+//     un-contracted tail; all are chosen by warp-uniform branches OUTSIDE the steady-state loop.
+template <int K, bool SCALE, bool EDGE, bool REV, bool EXACT, bool TMA>
 __device__ __forceinline__ void tb_block(float4 (&w)[K][3], float4 (&dr)[TB<K>::RD], TBStream& st,
-                                         float4* __restrict__ ring, const TBSeg& sg, const int W4,
+                                         const float4* __restrict__ ring, const TBTma& tm, const int W4,
                                          const int ye, const int y0, const int y1, const int H,
                                          const bool rev, const bool lane_out, const float scale) {
     using T = TB<K>;
+    const float4* srow = ring;
+    if (TMA) {
+        mbar_wait(tm.bars + st.stg, st.phase, tm.err);
+        srow = ring + st.stg * T::STAGE4;
+    }
 #pragma unroll
     for (int ph = 0; ph < 3; ++ph) {
-        // ---- level 0: wait for the oldest staged row, read it, refill a slot ----------------------
+        // ---- level 0: the oldest staged row ---------------------------------------------------------
         float4 in, dv;
         if (TMA) {
-            mbar_wait(sg.bars + st.slot, st.phase, sg.err);
-            in = lds128(st.stage);
-            dv = lds128(st.stage + T::D * 32);
-            // refill the slot consumed ONE STEP AGO (its values have been used, so every lane's
-            // reads of it have completed); D-1 rows stay in flight
-            __syncwarp();
-            if (sg.lane == 0) {
-                const int t = (st.slot == 0) ? T::D - 1 : st.slot - 1;
-                mbar_expect_tx(sg.bars + t, 2 * sg.bytes);
-                bulk_g2s(sg.slots + t * 32 + sg.dst4, st.pseg, sg.bytes, sg.bars + t);
-                bulk_g2s(sg.slots + (T::D + t) * 32 + sg.dst4, st.dseg, sg.bytes, sg.bars + t);
-            }
-            if (st.rload < ye) { ++st.rload; st.pseg += sg.W; st.dseg += sg.W; }
-            if (st.slot + 1 == T::D) { st.slot = 0; st.phase ^= 1u; } else { ++st.slot; }
+            in = lds128(srow + ph * 32);
+            dv = lds128(srow + (3 + ph) * 32);
         } else {
             cp_async_wait<T::D - 1>();
             in = lds128(st.stage);
             dv = lds128(st.stage + T::D * 32);
-            cp_async16(st.stage, st.pl);
-            cp_async16(st.stage + T::D * 32, st.dl);
+            cp_async16(const_cast<float4*>(st.stage), st.pl);
+            cp_async16(const_cast<float4*>(st.stage) + T::D * 32, st.dl);
             cp_async_commit();
             if (st.rload < ye) { ++st.rload; st.pl += W4; st.dl += W4; }   // loads clamp to row ye
             st.slot = (st.slot + 1 == T::D) ? 0 : st.slot + 1;
+            st.stage = ring + st.slot * 32;
         }
-        st.stage = ring + st.slot * 32;
         if (REV) { in = rev4(in, rev); dv = rev4(dv, rev); }
         if (SCALE) {
             in.x = scale * in.x; in.y = scale * in.y; in.z = scale * in.z; in.w = scale * in.w;
+        }
+        if (!EXACT) {                             // d' = -0.25 * d, exact outside the flagged cells
+            const u64 nq = pack2(-0.25f, -0.25f);
+            u64 a = mul2(pack2(dv.x, dv.y), nq), b = mul2(pack2(dv.z, dv.w), nq);
+            unpack2(a, dv.x, dv.y); unpack2(b, dv.z, dv.w);
         }
         w[0][(ph + 2) % 3] = in;
         dr[K + ph] = dv;
@@ -301,10 +345,10 @@ __device__ __forceinline__ void tb_block(float4 (&w)[K][3], float4 (&dr)[TB<K>::
                 if (r == H - 1) above = c;        //                p[i,H]  = p[i,H-1]
             }
             const float4 d = dr[K + ph - t];      // div row staged t steps ago
-            const float4 o = jacobi4(below, c, above, d);
+            const float4 o = jacobi4<EXACT>(below, c, above, d);
             if (t < K) {
                 w[t][(ph + 2) % 3] = o;
-            } else if (lane_out && st.rout >= y0 && st.rout < y1) {
+            } else if (lane_out && (unsigned)(st.rout - y0) < (unsigned)(y1 - y0)) {
                 *st.op = o;
             }
         }
@@ -313,19 +357,30 @@ __device__ __forceinline__ void tb_block(float4 (&w)[K][3], float4 (&dr)[TB<K>::
     }
 #pragma unroll
     for (int j = 0; j < K; ++j) dr[j] = dr[j + 3];
+    if (TMA) {
+        // Refill the stage consumed ONE BLOCK AGO with the box NS-1 blocks ahead: every value read
+        // from it has been used by now, so all lanes' reads of it have completed.
+        __syncwarp();
+        if (tm.lane == 0) {
+            const int q = (st.stg == 0) ? T::NS - 1 : st.stg - 1;
+            float4* dst = tm.slots + q * T::STAGE4;
+            mbar_expect_tx(tm.bars + q, 2u * 3u * 512u);
+            tma_load_2d(dst, tm.tm_p, tm.x0, st.yfill, tm.bars + q);
+            tma_load_2d(dst + 3 * 32, tm.tm_d, tm.x0, st.yfill, tm.bars + q);
+        }
+        st.yfill += 3;
+        if (st.stg + 1 == T::NS) { st.stg = 0; st.phase ^= 1u; } else { ++st.stg; }
+    }
 }
 
-template <int K, bool SCALE, bool REV, bool TMA>
-__device__ __forceinline__ void tb_stream(const JacobiArgs& a, float4* __restrict__ smem4, const int lane,
-                                          const int x0, const int lc, const int gx, const bool rev,
-                                          const bool lane_out, const int cy) {
+template <int K, bool SCALE, bool REV, bool EXACT, bool TMA>
+__device__ __forceinline__ void tb_stream(const JacobiArgs& a, const void* tm_p, const void* tm_d,
+                                          float4* __restrict__ smem4, const int lane, const int x0,
+                                          const int lc, const int gx, const bool rev,
+                                          const bool lane_out, const int y0, const int y1,
+                                          const int ys, const int ye) {
     using T = TB<K>;
     const int W = a.W, H = a.H, W4 = W >> 2;
-    // ---- y geometry of this warp's stream ----------------------------------------------------------
-    const int y0 = a.out_lo + cy * a.rows_per_chunk;
-    const int y1 = min(y0 + a.rows_per_chunk, a.out_hi);
-    const int ys = max(y0 - K, 0);                    // first input row
-    const int ye = min(y1 - 1 + K, H - 1);            // last input row (loads clamp to it)
     const int nsteps = y1 - ys + K;                   // level K emits row ys+s-K at step s
 
     const ptrdiff_t base = -(ptrdiff_t)a.row_off * W4;
@@ -341,42 +396,34 @@ __device__ __forceinline__ void tb_stream(const JacobiArgs& a, float4* __restric
 #pragma unroll
     for (int q = 0; q < T::RD; ++q) dr[q] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    TBStream st;
-    TBSeg sg{};
-    float4* ring;
-    st.rload = ys;
-    st.slot = 0;
-    st.phase = 0;
+    TBStream st{};
+    TBTma tm{};
+    const float4* ring;
     if (TMA) {
-        // the window's in-grid column segment [cs, ce); every lane reads its (mirrored / clamped)
-        // column group out of the staged segment
-        const int cs = max(x0, 0), ce = min(x0 + 128, W);
-        const int lcs = min(max(lc, cs), ce - 4);
-        sg.bytes = (unsigned)(ce - cs) * 4u;
-        sg.dst4 = (cs - x0) >> 2;
-        sg.W = W;
-        sg.bars = reinterpret_cast<unsigned long long*>(smem4 + 2 * T::D * 32);
-        sg.slots = smem4;
-        sg.lane = lane;
-        sg.err = a.err;
-        ring = smem4 + ((lcs - x0) >> 2);
-        st.pseg = a.pin + ((ptrdiff_t)ys - a.row_off) * W + cs;
-        st.dseg = a.div + ((ptrdiff_t)ys - a.row_off) * W + cs;
+        // every lane reads its (mirrored / clamped) column group out of the staged 128-column box
+        ring = smem4 + ((lc - x0) >> 2);
+        tm.tm_p = tm_p; tm.tm_d = tm_d;
+        tm.bars = reinterpret_cast<unsigned long long*>(smem4 + T::NS * T::STAGE4);
+        tm.slots = smem4;
+        tm.x0 = x0; tm.lane = lane; tm.err = a.err;
+        st.stg = 0; st.phase = 0;
+        st.yfill = ys - a.row_off;
         if (lane == 0) {
 #pragma unroll
-            for (int q = 0; q < T::D; ++q) mbar_init(sg.bars + q, 1);
+            for (int q = 0; q < T::NS; ++q) mbar_init(tm.bars + q, 1);
             mbar_fence_init();
         }
         __syncwarp();
-        // fill slots 0 .. D-2 with rows ys .. ys+D-2 (clamped to ye); slot D-1 is filled at step 0
+        // boxes of blocks 0 .. NS-2 into stages 0 .. NS-2; stage NS-1 is filled at the end of block 0
 #pragma unroll
-        for (int q = 0; q < T::D - 1; ++q) {
+        for (int q = 0; q < T::NS - 1; ++q) {
             if (lane == 0) {
-                mbar_expect_tx(sg.bars + q, 2 * sg.bytes);
-                bulk_g2s(sg.slots + q * 32 + sg.dst4, st.pseg, sg.bytes, sg.bars + q);
-                bulk_g2s(sg.slots + (T::D + q) * 32 + sg.dst4, st.dseg, sg.bytes, sg.bars + q);
+                float4* dst = tm.slots + q * T::STAGE4;
+                mbar_expect_tx(tm.bars + q, 2u * 3u * 512u);
+                tma_load_2d(dst, tm_p, x0, st.yfill, tm.bars + q);
+                tma_load_2d(dst + 3 * 32, tm_d, x0, st.yfill, tm.bars + q);
             }
-            if (st.rload < ye) { ++st.rload; st.pseg += W; st.dseg += W; }
+            st.yfill += 3;
         }
     } else {
         ring = smem4 + lane;                          // p slot q at ring[q*32], div at ring[(D+q)*32]
@@ -384,16 +431,17 @@ __device__ __forceinline__ void tb_stream(const JacobiArgs& a, float4* __restric
         const float4* Dg = reinterpret_cast<const float4*>(a.div) + base + (lc >> 2);
         st.pl = Pg + (ptrdiff_t)ys * W4;
         st.dl = Dg + (ptrdiff_t)ys * W4;
+        st.rload = ys; st.slot = 0;
         // fill the staging ring: rows ys .. ys+D-1 (clamped to ye), one cp.async group per row
 #pragma unroll
         for (int q = 0; q < T::D; ++q) {
-            cp_async16(ring + q * 32, st.pl);
-            cp_async16(ring + (T::D + q) * 32, st.dl);
+            cp_async16(smem4 + lane + q * 32, st.pl);
+            cp_async16(smem4 + lane + (T::D + q) * 32, st.dl);
             cp_async_commit();
             if (st.rload < ye) { ++st.rload; st.pl += W4; st.dl += W4; }
         }
+        st.stage = ring;
     }
-    st.stage = ring;
     st.rout = ys - K;
     st.op = Og + (ptrdiff_t)st.rout * W4;             // only dereferenced for rows in [y0, y1)
 
@@ -406,17 +454,17 @@ __device__ __forceinline__ void tb_stream(const JacobiArgs& a, float4* __restric
     for (int part = 0; part < 2; ++part) {
 #pragma unroll 1
         for (; s0 < nsteps && ((ys + s0 - K <= 0) || (ys + s0 + 2 >= H - 1)); s0 += 3)
-            tb_block<K, SCALE, true, REV, TMA>(w, dr, st, ring, sg, W4, ye, y0, y1, H, rev, lane_out, a.scale);
+            tb_block<K, SCALE, true, REV, EXACT, TMA>(w, dr, st, ring, tm, W4, ye, y0, y1, H, rev, lane_out, a.scale);
 #pragma unroll 1
         for (; s0 < nsteps && !((ys + s0 - K <= 0) || (ys + s0 + 2 >= H - 1)); s0 += 3)
-            tb_block<K, SCALE, false, REV, TMA>(w, dr, st, ring, sg, W4, ye, y0, y1, H, rev, lane_out, a.scale);
+            tb_block<K, SCALE, false, REV, EXACT, TMA>(w, dr, st, ring, tm, W4, ye, y0, y1, H, rev, lane_out, a.scale);
     }
     // drain the over-fetched tail before the CTA (and its shared memory) goes away
     if (TMA) {
 #pragma unroll 1
-        for (int q = 0; q < T::D - 1; ++q) {
-            mbar_wait(sg.bars + st.slot, st.phase, sg.err);
-            if (st.slot + 1 == T::D) { st.slot = 0; st.phase ^= 1u; } else { ++st.slot; }
+        for (int q = 0; q < T::NS - 1; ++q) {
+            mbar_wait(tm.bars + st.stg, st.phase, tm.err);
+            if (st.stg + 1 == T::NS) { st.stg = 0; st.phase ^= 1u; } else { ++st.stg; }
         }
     } else {
         cp_async_wait<0>();
@@ -426,17 +474,20 @@ __device__ __forceinline__ void tb_stream(const JacobiArgs& a, float4* __restric
 // One warp per CTA: every quantity that steers control flow derives from blockIdx and kernel
 // arguments only, so the compiler can prove the warp converged at each shuffle (no WARPSYNC /
 // BSSY scaffolding) and keeps loop state in uniform registers.
+#ifndef FLUID_TB_MINBLOCKS
+#define FLUID_TB_MINBLOCKS 1     // tuning builds: resident CTAs per SM the register allocation must allow
+#endif
 template <int K, bool SCALE, bool TMA>
-__global__ void __launch_bounds__(32) jacobi_tb_kernel(JacobiArgs a) {
+__global__ void __launch_bounds__(32, FLUID_TB_MINBLOCKS) jacobi_tb_kernel(JacobiArgs a, const __grid_constant__ TmapPair maps) {
     using T = TB<K>;
-    extern __shared__ __align__(16) float4 smem4[];
+    extern __shared__ __align__(128) float4 smem4[];
     const int lane = threadIdx.x;
     const int nxw = (a.W + T::VALID - 1) / T::VALID;
     const int wid = blockIdx.x;
     const int wx = wid % nxw, cy = wid / nxw;
 
     // ---- x geometry of this lane: mirrored / clamped float4 column group ------------------------
-    const int W = a.W;
+    const int W = a.W, H = a.H;
     const int gx = wx * T::VALID - T::HX + 4 * lane;  // first global column of this lane
     int lc = gx;
     bool rev = false;
@@ -446,8 +497,48 @@ __global__ void __launch_bounds__(32) jacobi_tb_kernel(JacobiArgs a) {
     const bool any_rev = (wx == 0) || ((wx + 1) * T::VALID + T::HX > W);   // warp-uniform
     const bool lane_out = (lane >= T::HX / 4) && (lane < 32 - T::HX / 4) && (gx >= 0) && (gx < W);
     const int x0 = wx * T::VALID - T::HX;
-    if (any_rev) tb_stream<K, SCALE, true, TMA>(a, smem4, lane, x0, lc, gx, rev, lane_out, cy);
-    else tb_stream<K, SCALE, false, TMA>(a, smem4, lane, x0, lc, gx, rev, lane_out, cy);
+
+    // ---- y geometry of this warp's stream ----------------------------------------------------------
+    const int y0 = a.out_lo + cy * a.rows_per_chunk;
+    const int y1 = min(y0 + a.rows_per_chunk, a.out_hi);
+    const int ys = max(y0 - K, 0);                    // first input row
+    const int ye = min(y1 - 1 + K, H - 1);            // last input row
+
+    // ---- does the divergence this stream reads hold a value that defeats the fma contraction? ----
+    bool exact = false;
+#ifndef FLUID_TB_NO_EXACT          // tuning builds only: measures what the second instantiation costs in code size
+    if (a.tiny_map) {
+        const int mw = tiny_map_w(W);
+        const int cx0 = max(x0, 0) / TINY_CW, cx1 = min(x0 + 127, W - 1) / TINY_CW;
+        const int cy0 = ys / TINY_CH, cy1 = ye / TINY_CH;
+        const int ncx = cx1 - cx0 + 1, n = ncx * (cy1 - cy0 + 1);
+        unsigned f = 0;
+        for (int k = lane; k < n; k += 32) f |= a.tiny_map[(cy0 + k / ncx) * mw + cx0 + k % ncx];
+        exact = __any_sync(0xffffffffu, f != 0);
+    }
+#endif
+    const void* tp = &maps.p;
+    const void* td = &maps.d;
+    if (exact) {
+        if (any_rev) tb_stream<K, SCALE, true, true, TMA>(a, tp, td, smem4, lane, x0, lc, gx, rev, lane_out, y0, y1, ys, ye);
+        else tb_stream<K, SCALE, false, true, TMA>(a, tp, td, smem4, lane, x0, lc, gx, rev, lane_out, y0, y1, ys, ye);
+    } else {
+        if (any_rev) tb_stream<K, SCALE, true, false, TMA>(a, tp, td, smem4, lane, x0, lc, gx, rev, lane_out, y0, y1, ys, ye);
+        else tb_stream<K, SCALE, false, false, TMA>(a, tp, td, smem4, lane, x0, lc, gx, rev, lane_out, y0, y1, ys, ye);
+    }
+}
+
+// ---- producers of the tiny-divergence map ----------------------------------------------------------
+// Host-written divergence (fluid_write, fluid_pressure_solve_host) and ghost rows received from a
+// neighbour are scanned by this kernel; the kernels that COMPUTE divergence flag cells themselves.
+// The map must have been zeroed for the rows being scanned (cudaMemsetAsync by the caller).
+__global__ void __launch_bounds__(256) tiny_scan_kernel(const float* __restrict__ div, unsigned char* __restrict__ map,
+                                                        int W, int row_off, int j_lo, int j_hi) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = j_lo + blockIdx.y;
+    if (i >= W || j >= j_hi) return;
+    if (is_tiny_div(__ldg(div + (size_t)(j - row_off) * W + i)))
+        map[(j / TINY_CH) * tiny_map_w(W) + i / TINY_CW] = 1;
 }
 
 }  // namespace fk
