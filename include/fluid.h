@@ -197,6 +197,25 @@ int fluid_pressure_solve_host(fluid_t* h, const float* div_host, float* pressure
 int fluid_render(fluid_t* h, int width, int height, int shading, float back_r, float back_g,
                  float back_b, float* host_rgba, size_t n_floats);
 
+/* The same with the reference's desktop defaults SHADING = BLOOM = SUNRAYS = true (S:70-84):
+ * applyBloom (S:1350-1394), applySunrays + blur (S:1396-1419), then the display shader with all three
+ * keywords.  fx = the BLOOM_* / SUNRAYS_* keys of `config`; dither_rgb = the dw x dh RGB dithering
+ * texture (LDR_LLL1_0.png / 255, first image row first, S:1128-1158).  host_bloom (bloom FBO,
+ * getResolution(BLOOM_RESOLUTION) x RGBA) and host_sunrays (getResolution(SUNRAYS_RESOLUTION) x R)
+ * may be NULL. */
+typedef struct fluid_postfx {
+    int32_t bloom_iterations;    /* S:77 default 8    */
+    int32_t bloom_resolution;    /* S:78 default 256  */
+    double bloom_intensity;      /* S:79 default 0.8  (double: knee / curve are derived in double like the JS) */
+    double bloom_threshold;      /* S:80 default 0.6  */
+    double bloom_soft_knee;      /* S:81 default 0.7  */
+    int32_t sunrays_resolution;  /* S:83 default 196  */
+    double sunrays_weight;       /* S:84 default 1.0  */
+} fluid_postfx;
+int fluid_render_postfx(fluid_t* h, int width, int height, const fluid_postfx* fx, const float* dither_rgb,
+                        int dw, int dh, float back_r, float back_g, float back_b, float* host_rgba,
+                        size_t n_floats, float* host_bloom, float* host_sunrays);
+
 int fluid_sync(fluid_t* h);
 int fluid_timing_last(fluid_t* h, fluid_timing* out);
 

@@ -433,3 +433,26 @@ def test_render_display_bitwise_vs_oracle(pkg, oracle, Wd, Hd, w, h):
         s.writeField("dye", g["in_dye"]); s.config["BACK_COLOR"] = {"r": 30, "g": 60, "b": 200}
         assert bits_equal(s.render(128, 128), g["shaded"])
         s.close()
+
+
+@pytest.mark.parametrize("name", ["postfx_64_to_128", "postfx_48x32_to_50x75"])
+def test_render_postfx_vs_oracle_and_executed_shaders(pkg, oracle, name):
+    """render() with SHADING + BLOOM + SUNRAYS: bloom FBO and sunrays texture bit-identical to the
+    oracle, final frame within the pow() tolerance, and within the golden's tolerance of the executed
+    reference shaders."""
+    g = golden(name)
+    Wd, Hd, w, h = (int(g[k]) for k in ("Wd", "Hd", "w", "h"))
+    fxcfg = dict(BLOOM_RESOLUTION=int(g["bloom_res"]), SUNRAYS_RESOLUTION=int(g["sun_res"]))
+    dither = g["dither"].astype(np.float32)
+    s = make(pkg, 16, 16, Wd, Hd)
+    s.writeField("dye", g["in_dye"])
+    s.config.update(BLOOM=True, SUNRAYS=True, SHADING=True, BACK_COLOR={"r": 10, "g": 20, "b": 30}, **fxcfg)
+    s.dithering = dither
+    got = s.render(w, h)
+    ref = oracle.render_postfx(g["in_dye"], w, h, dither, cfg=fxcfg, back_rgb=(10 / 255, 20 / 255, 30 / 255))
+    assert bits_equal(s.last_bloom, ref["bloom"])
+    assert bits_equal(s.last_sunrays, ref["sunrays"])
+    assert max_rel(got, ref["target"]) < 5e-6                 # powf: CUDA vs glibc last-place differences
+    assert max_rel(got, g["target"]) < 3e-4
+    assert bits_equal(s.readField("dye"), g["in_dye"])        # the mask scribbles on dye.write only (S:1300)
+    s.close()

@@ -22,7 +22,7 @@ SYMBOLS = [
     "fluid_pass_divergence", "fluid_pass_clear_pressure", "fluid_pass_jacobi",
     "fluid_pass_pressure_solve", "fluid_pass_gradient_subtract", "fluid_pass_advect_velocity",
     "fluid_pass_advect_dye", "fluid_pass_curl_vorticity_divergence", "fluid_field_elems",
-    "fluid_field_dims", "fluid_read", "fluid_write", "fluid_pressure_solve_host", "fluid_render", "fluid_sync",
+    "fluid_field_dims", "fluid_read", "fluid_write", "fluid_pressure_solve_host", "fluid_render", "fluid_render_postfx", "fluid_sync",
     "fluid_timing_last", "fluid_mark", "fluid_elapsed_ms", "fluid_launch_count", "fluid_device_ptr",
     "fluid_last_error",
 ]
@@ -51,6 +51,12 @@ class Config(C.Structure):
                 ("pressure", C.c_float), ("pressure_iterations", C.c_int32), ("curl", C.c_float),
                 ("splat_radius", C.c_float), ("aspect", C.c_float), ("device", C.c_int32),
                 ("flags", C.c_uint32), ("jacobi_block", C.c_int32)]
+
+
+class PostFX(C.Structure):
+    _fields_ = [("bloom_iterations", C.c_int32), ("bloom_resolution", C.c_int32), ("bloom_intensity", C.c_double),
+                ("bloom_threshold", C.c_double), ("bloom_soft_knee", C.c_double), ("sunrays_resolution", C.c_int32),
+                ("sunrays_weight", C.c_double)]
 
 
 class Timing(C.Structure):
@@ -110,6 +116,7 @@ def lib():
     L.fluid_write.argtypes = [vp, i, vp, sz]
     L.fluid_pressure_solve_host.argtypes = [vp, vp, vp, i]
     L.fluid_render.argtypes = [vp, i, i, i, f, f, f, vp, sz]
+    L.fluid_render_postfx.argtypes = [vp, i, i, C.POINTER(PostFX), vp, i, i, f, f, f, vp, sz, vp, vp]
     L.fluid_sync.argtypes = [vp]
     L.fluid_timing_last.argtypes = [vp, C.POINTER(Timing)]
     L.fluid_mark.argtypes = [vp, i]

@@ -21,6 +21,7 @@
 #include "nccl_dl.h"
 #include "passes.cuh"
 #include "stream_passes.cuh"
+#include "postfx.cuh"
 
 namespace {
 
@@ -1172,6 +1173,92 @@ int fluid_render(fluid_t* h, int width, int height, int shading, float back_r, f
     CU(cudaMemcpyAsync(host_rgba, h->frame, cells * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return FLUID_OK;
+}
+
+// render(null) of S:1296-1317 with config.SHADING = BLOOM = SUNRAYS = true (the reference's desktop
+// defaults S:70-84), TRANSPARENT = false: applyBloom (S:1350-1394), applySunrays + blur(…, 1)
+// (S:1396-1419; the mask is drawn into dye.write exactly like S:1300), drawColor, drawDisplay.
+// FBO sizes follow initBloomFramebuffers / initSunraysFramebuffers (S:1012-1043).
+int fluid_render_postfx(fluid_t* h, int width, int height, const fluid_postfx* fx, const float* dither_rgb,
+                        int dw, int dh, float back_r, float back_g, float back_b, float* host_rgba,
+                        size_t n_floats, float* host_bloom, float* host_sunrays) {
+    if (!h || !fx || !dither_rgb || !host_rgba || width < 1 || height < 1 || dw < 1 || dh < 1)
+        return fail(h, FLUID_ERR_INVALID, "bad argument");
+    if (h->slab()) return not_on_slab(h, "fluid_render_postfx");
+    const size_t cells = (size_t)width * height;
+    if (n_floats != 4 * cells) return fail(h, FLUID_ERR_INVALID, "render target has %zu floats, caller passed %zu", 4 * cells, n_floats);
+    int bw, bh, sw, sh;
+    fluid_get_resolution(fx->bloom_resolution, width, height, &bw, &bh);
+    fluid_get_resolution(fx->sunrays_resolution, width, height, &sw, &sh);
+    if (bw < 1 || bh < 1 || sw < 1 || sh < 1) return fail(h, FLUID_ERR_INVALID, "bad post-FX resolution");
+    std::vector<void*> tmp;
+    auto dalloc = [&](size_t bytes) -> void* { void* p = nullptr; if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr; tmp.push_back(p); return p; };
+    auto cleanup = [&]() { cudaStreamSynchronize(h->stream); for (void* p : tmp) cudaFree(p); };
+    int rc = FLUID_OK;
+    auto body = [&]() -> int {
+        if (cells > h->frame_cells) {
+            CU(cudaStreamSynchronize(h->stream));
+            cudaFree(h->frame); h->frame = nullptr; h->frame_cells = 0;
+            CU(cudaMalloc((void**)&h->frame, cells * sizeof(float4)));
+            h->frame_cells = cells;
+        }
+        const int Wd = h->cfg.dye_w, Hd = h->cfg.dye_h;
+        dim3 b(32, 8);
+        float4* bloom = (float4*)dalloc((size_t)bw * bh * sizeof(float4));
+        float* sun = (float*)dalloc((size_t)sw * sh * sizeof(float));
+        float* sun2 = (float*)dalloc((size_t)sw * sh * sizeof(float));
+        float* dith = (float*)dalloc((size_t)dw * dh * 3 * sizeof(float));
+        if (!bloom || !sun || !sun2 || !dith) return fail(h, FLUID_ERR_NOMEM, "out of device memory for the post-FX targets");
+        CU(cudaMemcpyAsync(dith, dither_rgb, (size_t)dw * dh * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        fill_alpha_kernel<<<(unsigned)(((size_t)bw * bh + 255) / 256), 256, 0, h->stream>>>(bloom, (size_t)bw * bh);   // createFBO clear
+        // ---- applyBloom(dye.read, bloom) ----------------------------------------------------------
+        struct Lv { float4* p; int w, h; };
+        std::vector<Lv> pyr;
+        for (int i = 0; i < fx->bloom_iterations; ++i) {
+            const int pw = bw >> (i + 1), ph = bh >> (i + 1);
+            if (pw < 2 || ph < 2) break;
+            float4* p = (float4*)dalloc((size_t)pw * ph * sizeof(float4));
+            if (!p) return fail(h, FLUID_ERR_NOMEM, "out of device memory for the bloom pyramid");
+            pyr.push_back({p, pw, ph});
+        }
+        int nk = 1;
+        if (pyr.size() >= 2) {
+            const double knee = fx->bloom_threshold * fx->bloom_soft_knee + 0.0001;
+            bloom_prefilter_kernel<<<grid2d(bw, bh, b), b, 0, h->stream>>>(
+                (const float4*)h->dye.read, Wd, Hd, bloom, bw, bh, (float)(fx->bloom_threshold - knee),
+                (float)(knee * 2), (float)(0.25 / knee), (float)fx->bloom_threshold);
+            ++nk;
+            Lv last{bloom, bw, bh};
+            for (auto& d : pyr) {
+                box4_kernel<<<grid2d(d.w, d.h, b), b, 0, h->stream>>>(last.p, last.w, last.h, d.p, d.w, d.h, 1.0f, 0);
+                last = d; ++nk;
+            }
+            for (int i = (int)pyr.size() - 2; i >= 0; --i) {
+                box4_kernel<<<grid2d(pyr[i].w, pyr[i].h, b), b, 0, h->stream>>>(last.p, last.w, last.h, pyr[i].p, pyr[i].w, pyr[i].h, 1.0f, 1);
+                last = pyr[i]; ++nk;
+            }
+            box4_kernel<<<grid2d(bw, bh, b), b, 0, h->stream>>>(last.p, last.w, last.h, bloom, bw, bh, (float)fx->bloom_intensity, 0);
+            ++nk;
+        }
+        // ---- applySunrays(dye.read, dye.write, sunrays); blur(sunrays, sunraysTemp, 1) ---------------
+        sunrays_mask_kernel<<<grid2d(Wd, Hd, b), b, 0, h->stream>>>((const float4*)h->dye.read, (float4*)h->dye.write, Wd, Hd);
+        sunrays_kernel<<<grid2d(sw, sh, b), b, 0, h->stream>>>((const float4*)h->dye.write, Wd, Hd, sun, sw, sh, (float)fx->sunrays_weight);
+        blur3_kernel<<<grid2d(sw, sh, b), b, 0, h->stream>>>(sun, sun2, sw, sh, (float)(1.0 / (double)sw), 0.0f);
+        blur3_kernel<<<grid2d(sw, sh, b), b, 0, h->stream>>>(sun2, sun, sw, sh, 0.0f, (float)(1.0 / (double)sh));
+        // ---- drawColor + drawDisplay ---------------------------------------------------------------------
+        display_full_kernel<<<grid2d(width, height, b), b, 0, h->stream>>>(
+            (const float4*)h->dye.read, Wd, Hd, bloom, bw, bh, sun, sw, sh, dith, dw, dh, h->frame, width, height,
+            back_r, back_g, back_b);
+        int r = check_launch(h, "post-FX kernels", nk + 5); if (r) return r;
+        CU(cudaMemcpyAsync(host_rgba, h->frame, cells * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+        if (host_bloom) CU(cudaMemcpyAsync(host_bloom, bloom, (size_t)bw * bh * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+        if (host_sunrays) CU(cudaMemcpyAsync(host_sunrays, sun, (size_t)sw * sh * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        return FLUID_OK;
+    };
+    rc = body();
+    cleanup();
+    return rc;
 }
 
 int fluid_sync(fluid_t* h) {

@@ -22,7 +22,7 @@ import time
 import numpy as np
 
 from . import _lib
-from ._lib import FIELD, PARAM, STAT, Config, FluidError, Timing
+from ._lib import FIELD, PARAM, STAT, Config, FluidError, PostFX, Timing
 
 
 def default_config() -> dict:
@@ -44,8 +44,15 @@ def default_config() -> dict:
         "PAUSED": False,
         "BACK_COLOR": {"r": 0, "g": 0, "b": 0},
         "TRANSPARENT": False,
-        "BLOOM": False,          # post-FX are not built (second half): render() refuses them
-        "SUNRAYS": False,
+        "BLOOM": False,          # reference default is true; needs `sim.dithering` (the 64x64 RGB texture), see render()
+        "BLOOM_ITERATIONS": 8,
+        "BLOOM_RESOLUTION": 256,
+        "BLOOM_INTENSITY": 0.8,
+        "BLOOM_THRESHOLD": 0.6,
+        "BLOOM_SOFT_KNEE": 0.7,
+        "SUNRAYS": False,        # reference default is true
+        "SUNRAYS_RESOLUTION": 196,
+        "SUNRAYS_WEIGHT": 1.0,
     }
 
 
@@ -337,11 +344,31 @@ class FluidSimulation:
         """render(target), S:1296-1317, for BLOOM = SUNRAYS = TRANSPARENT = false: background colour
         + shaded dye, (height, width, 4) float32 RGBA, row 0 = bottom.  Defaults to the canvas size
         (target == null branch, S:1332-1333)."""
-        if self.config.get("BLOOM") or self.config.get("SUNRAYS") or self.config.get("TRANSPARENT"):
-            raise NotImplementedError("bloom / sunrays / transparent display are not built (DESIGN.md: out of scope this round)")
         w = int(width or self.canvas["width"]); h = int(height or self.canvas["height"])
         bc = self.config["BACK_COLOR"]                       # normalizeColor, S:1599-1606
         out = np.empty((h, w, 4), np.float32)
+        cfg = self.config
+        if cfg.get("TRANSPARENT"):
+            raise NotImplementedError("TRANSPARENT (checkerboard) display is not built")
+        if cfg.get("BLOOM") or cfg.get("SUNRAYS"):
+            # built for the reference's default keyword set only: SHADING + BLOOM + SUNRAYS
+            if not (cfg.get("BLOOM") and cfg.get("SUNRAYS") and cfg.get("SHADING")):
+                raise NotImplementedError("post-FX are built for SHADING + BLOOM + SUNRAYS together (the reference defaults)")
+            dith = getattr(self, "dithering", None)
+            if dith is None:
+                raise ValueError("set sim.dithering to the (64, 64, 3) float RGB dithering texture (LDR_LLL1_0.png / 255)")
+            dith = np.ascontiguousarray(dith, np.float32)
+            fx = PostFX(int(cfg["BLOOM_ITERATIONS"]), int(cfg["BLOOM_RESOLUTION"]), float(cfg["BLOOM_INTENSITY"]),
+                        float(cfg["BLOOM_THRESHOLD"]), float(cfg["BLOOM_SOFT_KNEE"]), int(cfg["SUNRAYS_RESOLUTION"]),
+                        float(cfg["SUNRAYS_WEIGHT"]))
+            b = getResolution(cfg["BLOOM_RESOLUTION"], w, h); sr = getResolution(cfg["SUNRAYS_RESOLUTION"], w, h)
+            self.last_bloom = np.empty((b["height"], b["width"], 4), np.float32)
+            self.last_sunrays = np.empty((sr["height"], sr["width"]), np.float32)
+            self._check(self._L.fluid_render_postfx(
+                self._h, w, h, C.byref(fx), dith.ctypes.data_as(C.c_void_p), dith.shape[1], dith.shape[0],
+                bc["r"] / 255, bc["g"] / 255, bc["b"] / 255, out.ctypes.data_as(C.c_void_p), out.size,
+                self.last_bloom.ctypes.data_as(C.c_void_p), self.last_sunrays.ctypes.data_as(C.c_void_p)))
+            return out
         self._check(self._L.fluid_render(self._h, w, h, 1 if self.config["SHADING"] else 0,
                                          bc["r"] / 255, bc["g"] / 255, bc["b"] / 255,
                                          out.ctypes.data_as(C.c_void_p), out.size))
