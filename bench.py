@@ -490,6 +490,19 @@ def main():
                                  "unit": "GB/s", "frac": nach / peak, "ms_per_step": nms / nsteps,
                                  "updates_per_s": W * H * ITERS * nsteps / (nms * 1e-3)}
         nsim.close()
+        # ---- half-float storage (the reference's own texture format, S:138-147): 6 B per update ---------
+        hsim = pkg.FluidSimulation(cfg, 1024, 1024, device=local, flags=pkg.FLAG_HALF_STORAGE)
+        hsim.writeField("pressure", p0); hsim.writeField("divergence", d0)
+        hsolve = lambda: hsim.pass_("pressure_solve")
+        for _ in range(3): hsolve()
+        hsim.sync()
+        hsteps = max(3, min(args.steps, 20))
+        hms = time_steps(hsim, hsolve, hsteps); hsim.sync()
+        hach = 6 * W * H * ITERS * hsteps / (hms * 1e-3) / 1e9
+        out["roofline_half_storage"] = {"kernel": "hs::jacobi8_kernel (one sweep per launch, fp16 fields, fp32 arithmetic, RN-even on write)",
+                                        "bound": "hbm", "algorithmic_bytes_per_update": 6, "achieved": hach, "peak": peak, "unit": "GB/s",
+                                        "frac": hach / peak, "ms_per_step": hms / hsteps, "updates_per_s": W * H * ITERS * hsteps / (hms * 1e-3)}
+        hsim.close()
 
         # ---- whole step() on configs[1] and configs[2], with per-pass rooflines ------------------------
         ctx = {}

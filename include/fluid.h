@@ -73,6 +73,10 @@ typedef enum fluid_param {
 #define FLUID_FLAG_UNFUSED   0x1u /* run curl / vorticity / divergence as 3 separate passes      */
 #define FLUID_FLAG_NO_GRAPH  0x2u /* launch step() pass by pass instead of as one CUDA graph     */
 #define FLUID_FLAG_NAIVE_JACOBI 0x4u /* one Jacobi sweep per launch (the literal S:1262 loop)    */
+#define FLUID_FLAG_HALF_STORAGE 0x10u /* store every field as fp16 like the reference's textures (S:138-147,
+                                         S:986-1006): fp32 arithmetic, round-to-nearest-even on every pass
+                                         write, one launch per reference blit; single GPU; the ABI still
+                                         speaks fp32 (fluid_read widens, fluid_write narrows)              */
 #define FLUID_FLAG_TILED_PASSES 0x8u /* generation-1 kernels (one thread per fragment / smem tile) for
                                         curl-vorticity-divergence and gradientSubtract instead of the
                                         row-streaming ones (comparison + fallback path)              */

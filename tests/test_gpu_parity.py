@@ -456,3 +456,60 @@ def test_render_postfx_vs_oracle_and_executed_shaders(pkg, oracle, name):
     assert max_rel(got, g["target"]) < 3e-4
     assert bits_equal(s.readField("dye"), g["in_dye"])        # the mask scribbles on dye.write only (S:1300)
     s.close()
+
+
+def test_half_storage_every_pass_and_whole_steps_bitwise_vs_oracle(pkg, oracle):
+    """FLUID_FLAG_HALF_STORAGE: the reference's own storage format (half-float textures, S:138-147,
+    S:986-1006): fp32 arithmetic, fp16 round-to-nearest-even on every pass write.  Per pass and for
+    whole steps bit-identical to the oracle's half_storage mode (oracle_round_half after every blit)."""
+    O = oracle
+    W, H, Wd, Hd = 64, 48, 128, 96
+    v, dye, p = rand_fields(W, H, Wd, Hd, 77)
+    v, dye, p = O.round_half(v), O.round_half(dye), O.round_half(p)
+    s = make(pkg, W, H, Wd, Hd, flags=pkg.FLAG_HALF_STORAGE)
+    s.writeField("velocity", v); s.writeField("dye", dye); s.writeField("pressure", p)
+    assert bits_equal(s.readField("velocity"), v)                       # narrow + widen is the identity on fp16 values
+    R = O.round_half
+    s.pass_("curl"); c = s.readField("curl"); assert bits_equal(c, R(O.curl(v)))
+    s.pass_("vorticity", DT); v2 = s.readField("velocity"); assert bits_equal(v2, R(O.vorticity(v, c, 30.0, DT)))
+    s.pass_("divergence"); d = s.readField("divergence"); assert bits_equal(d, R(O.divergence(v2)))
+    s.pass_("clear_pressure"); p1 = s.readField("pressure"); assert bits_equal(p1, R(O.clear(p, 0.8)))
+    s.pass_("jacobi", 5); p2 = p1
+    for _ in range(5):
+        p2 = R(O.jacobi(p2, d, 1))
+    assert bits_equal(s.readField("pressure"), p2)
+    s.pass_("gradient_subtract"); v3 = s.readField("velocity"); assert bits_equal(v3, R(O.gradient_subtract(p2, v2)))
+    s.pass_("advect_velocity", DT); v4 = s.readField("velocity"); assert bits_equal(v4, R(O.advect(v3, v3, DT, 0.2)))
+    s.pass_("advect_dye", DT); assert bits_equal(s.readField("dye"), R(O.advect(v4, dye, DT, 1.0)))
+    s.close()
+    # whole steps (graph replay), 128^2 / 256^2, 20 iterations: every field, three steps
+    W = H = 128; Wd = Hd = 256
+    v, dye, p = rand_fields(W, H, Wd, Hd, 78)
+    v, dye, p = R(v), R(dye), R(p)
+    s = make(pkg, W, H, Wd, Hd, flags=pkg.FLAG_HALF_STORAGE)
+    ref = O.OracleSim(W, H, Wd, Hd, half_storage=True)
+    s.writeField("velocity", v); s.writeField("dye", dye); s.writeField("pressure", p)
+    ref.velocity, ref.dye, ref.pressure = v.copy(), dye.copy(), p.copy()
+    for _ in range(3):
+        s.step(DT); ref.step(DT)
+    for n in ("velocity", "dye", "pressure", "divergence", "curl"):
+        assert bits_equal(s.readField(n), getattr(ref, n)), n
+    # render() reads the fp16 dye through the fp32 display shader
+    assert bits_equal(s.render(64, 64), O.display(ref.dye, 64, 64, True, (0.0, 0.0, 0.0)))
+    s.close()
+
+
+def test_half_storage_vs_executed_reference_with_half_textures(pkg):
+    """The closest thing to a real WebGL run this repository can produce: the executed reference
+    shaders with LINEAR samplers and half-float textures (tests/golden/p4_linear_half_32.npz).
+    The half-storage mode must land within 1e-3 of it after one step (its only differences: expf /
+    LINEAR-weight last places ahead of the fp16 rounding) -- the fp32-storage mode is 4e-3 away."""
+    g = golden("p4_linear_half_32")
+    W, H, Wd, Hd = (int(g[k]) for k in ("W", "H", "Wd", "Hd"))
+    s = make(pkg, W, H, Wd, Hd, flags=pkg.FLAG_HALF_STORAGE)
+    for a in g["splats"]:
+        s.splat(*[float(x) for x in a[:4]], tuple(float(x) for x in a[4:]))
+    s.step(float(g["dt"]))
+    for n in ("velocity", "dye", "pressure"):
+        assert max_rel(s.readField(n), g[f"s1_{n}"]) < 1e-3, n
+    s.close()

@@ -35,12 +35,12 @@ def run(tag, env):
         print(f"{tag}: FAILED {out.stderr[-400:]}", flush=True)
 
 libs = {"default": None}
-for name in ("noexact", "m12"):
-    pth = os.path.join(ROOT, "webgl_fluid_simulation_b200", f"libfluid_b200_{name}.so")
-    if os.path.exists(pth):
-        libs[name] = pth
+import glob
+for pth in sorted(glob.glob(os.path.join(ROOT, "webgl_fluid_simulation_b200", "libfluid_b200_*.so"))):
+    libs[os.path.basename(pth)[len("libfluid_b200_"):-3]] = pth
 for lib, pth in libs.items():
     for stage in ("tma", "ldgsts"):
-        env = {"FLUID_TB_STAGE": stage, "TUNE_KB": "10"}
-        if pth: env["FLUID_B200_SO"] = pth
-        run(f"lib={lib} stage={stage}", env)
+        for warps in ((0,) if "192" not in lib else (0, 8, 9)):
+            env = {"FLUID_TB_STAGE": stage, "TUNE_KB": "10", "FLUID_JACOBI_WARPS": str(warps)}
+            if pth: env["FLUID_B200_SO"] = pth
+            run(f"lib={lib} stage={stage} warps={warps}", env)

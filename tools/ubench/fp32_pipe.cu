@@ -12,11 +12,12 @@ typedef unsigned long long u64;
 #endif
 #define BODY 4          // chain updates per loop iteration (per chain)
 
-enum Kind { K_FADD, K_FADD2, K_FFMA, K_FFMA2, K_FMUL2, K_MIX_1A2P, K_SHFL, K_FADD2_MOV, K_FADD_IMM, K_FFMA_IMM, K_NKIND };
+enum Kind { K_FADD, K_FADD2, K_FFMA, K_FFMA2, K_FMUL2, K_MIX_1A2P, K_SHFL, K_FADD2_MOV, K_FADD_IMM, K_FFMA_IMM, K_FADD2_DIST, K_FFMA2_DIST, K_FADD_DIST, K_NKIND };
 static const char* NAMES[] = {"FADD r,r,r", "FADD2 (add.f32x2)", "FFMA r,r,r,r", "FFMA2 (fma.f32x2)", "FMUL2 (mul.f32x2)",
-                              "mix 1 FADD : 2 FADD2", "SHFL.UP", "mix 1 FADD2 : 1 MOV", "FADD r,r,imm", "FFMA r,r,imm,r"};
+                              "mix 1 FADD : 2 FADD2", "SHFL.UP", "mix 1 FADD2 : 1 MOV", "FADD r,r,imm", "FFMA r,r,imm,r",
+                              "FADD2 distinct operands", "FFMA2 distinct operands", "FADD distinct operands"};
 // warp-instructions per loop iteration per thread
-static const int INSTR[] = {NCH * BODY, NCH * BODY, NCH * BODY, NCH * BODY, NCH * BODY, NCH * BODY, NCH * BODY, NCH * BODY, NCH * BODY, NCH * BODY};
+static const int INSTR[] = {NCH * BODY, NCH * BODY, NCH * BODY, NCH * BODY, NCH * BODY, NCH * BODY, NCH * BODY, NCH * BODY, NCH * BODY, NCH * BODY, NCH * BODY, NCH * BODY, NCH * BODY};
 
 template <int KIND>
 __global__ void bench(float* out, const float* in, int iters, u64* cycles) {
@@ -47,6 +48,10 @@ __global__ void bench(float* out, const float* in, int iters, u64* cycles) {
                     if (k % 3 == 0) asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(a[k]) : "f"(b));
                     else asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(p[k]) : "l"(pb));
                 }
+                // every operand a different register (pair): no operand-reuse cache hits, like real code
+                if (KIND == K_FADD2_DIST) asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(p[k]) : "l"(p[(k + 3) % NCH]), "l"(p[(k + 5) % NCH]));
+                if (KIND == K_FFMA2_DIST) asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(p[k]) : "l"(p[(k + 3) % NCH]), "l"(p[(k + 5) % NCH]), "l"(p[(k + 6) % NCH]));
+                if (KIND == K_FADD_DIST) asm volatile("add.rn.f32 %0, %1, %2;" : "=f"(a[k]) : "f"(a[(k + 3) % NCH]), "f"(a[(k + 5) % NCH]));
                 if (KIND == K_SHFL) asm volatile("shfl.sync.up.b32 %0, %0, 1, 0, 0xffffffff;" : "+f"(a[k]));
                 if (KIND == K_FADD2_MOV) {
                     if (k & 1) asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(p[k]) : "l"(pb));
@@ -100,6 +105,7 @@ int main() {
         run<K_FADD2>(w, out, in, cyc, nsm); run<K_FFMA>(w, out, in, cyc, nsm); run<K_FFMA_IMM>(w, out, in, cyc, nsm);
         run<K_FFMA2>(w, out, in, cyc, nsm); run<K_FMUL2>(w, out, in, cyc, nsm); run<K_MIX_1A2P>(w, out, in, cyc, nsm);
         run<K_SHFL>(w, out, in, cyc, nsm); run<K_FADD2_MOV>(w, out, in, cyc, nsm);
+        run<K_FADD_DIST>(w, out, in, cyc, nsm); run<K_FADD2_DIST>(w, out, in, cyc, nsm); run<K_FFMA2_DIST>(w, out, in, cyc, nsm);
         printf("\n");
     }
     cudaError_t e = cudaDeviceSynchronize();

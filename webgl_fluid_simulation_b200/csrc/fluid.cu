@@ -22,6 +22,7 @@
 #include "passes.cuh"
 #include "stream_passes.cuh"
 #include "postfx.cuh"
+#include "half_passes.cuh"
 
 namespace {
 
@@ -40,6 +41,9 @@ struct fluid {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;  // slab mode: halo exchange + boundary strips, overlapped with the interior launch
+    cudaStream_t active = nullptr;   // where halo / Jacobi launches go right now (== stream except inside that overlap)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t mark[2] = {nullptr, nullptr};
     cudaEvent_t tev[8] = {};
     Pair velocity, dye, pressure;    // float2 / float4 / float
@@ -49,6 +53,9 @@ struct fluid {
     uint64_t launches = 0;
     uint64_t jacobi_kernel_launches = 0;   // Jacobi kernels only (fluid_stat FLUID_STAT_JACOBI_LAUNCHES)
     uint64_t halo_kernel_launches = 0;     // halo_push / halo_wait kernels of the peer-memory transport
+    bool half = false;                     // FLUID_FLAG_HALF_STORAGE: fields are fp16 (half_passes.cuh), single GPU only
+    float* scratch = nullptr;              // half mode: fp32 staging of fluid_read / fluid_write / render
+    size_t scratch_floats = 0;
     float* dt_dev = nullptr;               // step()'s dt lives in device memory: one graph serves every dt
     unsigned char* tiny_map = nullptr;     // where divergence has 0 < |d| < 2^-123 (jacobi.cuh): 1 byte per 128x32 cells, GLOBAL rows
     size_t tiny_map_bytes = 0;
@@ -165,6 +172,21 @@ int set_dt(fluid_t* h, float dt) {
 
 #include "halo.cuh"
 
+// bytes per cell of each field: fp32 storage (float2 / float4 / float) or half storage (S:986-1006)
+inline size_t vbytes(const fluid_t* h) { return h->half ? 4 : 8; }
+inline size_t dbytes(const fluid_t* h) { return h->half ? 8 : 16; }
+inline size_t sbytes(const fluid_t* h) { return h->half ? 2 : 4; }
+int need_scratch(fluid_t* h, size_t floats) {
+    if (floats <= h->scratch_floats) return FLUID_OK;
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(h->scratch); h->scratch = nullptr; h->scratch_floats = 0;
+    CU(cudaMalloc((void**)&h->scratch, floats * sizeof(float)));
+    h->scratch_floats = floats;
+    return FLUID_OK;
+}
+inline dim3 hs_grid(int W, int H) { return dim3((W + 63) / 64, (H + 3) / 4); }
+const dim3 HS_BLOCK(64, 4);
+
 // ---- the tiny-divergence map (jacobi.cuh): one byte per 128 x 32 cells of the GLOBAL grid -------------
 int alloc_tiny_map(fluid_t* h) {
     cudaFree(h->tiny_map); h->tiny_map = nullptr;
@@ -182,7 +204,7 @@ int clear_tiny_map(fluid_t* h) {
 int scan_tiny(fluid_t* h, int j_lo, int j_hi) {
     if (j_hi <= j_lo) return FLUID_OK;
     dim3 b(256), g((h->cfg.sim_w + 255) / 256, j_hi - j_lo);
-    tiny_scan_kernel<<<g, b, 0, h->stream>>>(h->divergence, h->tiny_map, h->cfg.sim_w, h->roff, j_lo, j_hi);
+    tiny_scan_kernel<<<g, b, 0, h->active>>>(h->divergence, h->tiny_map, h->cfg.sim_w, h->roff, j_lo, j_hi);
     return check_launch(h, "tiny_scan_kernel");
 }
 
@@ -221,7 +243,7 @@ bool encode_rows_map(CUtensorMap* tm, void* base, int W, int rows) {
 // (re)build the tensor maps after the pressure / divergence buffers were allocated
 void build_tmaps(fluid_t* h) {
     h->tmaps.ok = false;
-    if (h->cfg.sim_w % 4 != 0 || h->cfg.sim_w < 16) return;
+    if (h->half || h->cfg.sim_w % 4 != 0 || h->cfg.sim_w < 16) return;
     const int rows = h->lrows();
     h->tmaps.p_ptr[0] = h->pressure.read; h->tmaps.p_ptr[1] = h->pressure.write;
     h->tmaps.ok = encode_rows_map(&h->tmaps.p[0], h->pressure.read, h->cfg.sim_w, rows) &&
@@ -240,16 +262,17 @@ template <int K, bool SCALE>
 int launch_tb(fluid_t* h, const JacobiArgs& a) {
     using T = TB<K>;
     const int nxw = (a.W + T::VALID - 1) / T::VALID;
-    const int nch = (a.out_hi - a.out_lo + a.rows_per_chunk - 1) / a.rows_per_chunk;
+    int nch = (a.out_hi - a.out_lo + a.rows_per_chunk - 1) / a.rows_per_chunk;
+    if (a.nch1 > 0) nch = a.nch1 + (a.seg2_hi - a.seg2_lo + a.rows_per_chunk - 1) / a.rows_per_chunk;
     TmapPair maps;
     memset(&maps, 0, sizeof maps);
     if (tb_use_tma(h)) {
         const int k = (a.pin == h->tmaps.p_ptr[0]) ? 0 : 1;
         memcpy(maps.p, &h->tmaps.p[k], sizeof(CUtensorMap));
         memcpy(maps.d, &h->tmaps.d, sizeof(CUtensorMap));
-        jacobi_tb_kernel<K, SCALE, true><<<nxw * nch, 32, T::SMEM_TMA, h->stream>>>(a, maps);   // one warp per CTA
+        jacobi_tb_kernel<K, SCALE, true><<<nxw * nch, 32, T::SMEM_TMA, h->active>>>(a, maps);   // one warp per CTA
     } else {
-        jacobi_tb_kernel<K, SCALE, false><<<nxw * nch, 32, T::SMEM_LDGSTS, h->stream>>>(a, maps);
+        jacobi_tb_kernel<K, SCALE, false><<<nxw * nch, 32, T::SMEM_LDGSTS, h->active>>>(a, maps);
     }
     ++h->jacobi_kernel_launches;
     return check_launch(h, "jacobi_tb_kernel");
@@ -263,7 +286,7 @@ int launch_tb_k(fluid_t* h, const JacobiArgs& a, bool scale) {
 // rows per warp stream: enough chunks that every SM holds its full complement of resident warps
 // (single wave), rounded so that a stream's step count R + 2K is a multiple of the unroll U.
 template <int K>
-int tb_rows(const fluid_t* h, int W, int rows) {
+int tb_rows(const fluid_t* h, int W, int rows, int reserve = 0) {
     if (h->jacobi_rows_override > 0) return h->jacobi_rows_override;
     using T = TB<K>;
     const int nxw = (W + T::VALID - 1) / T::VALID;
@@ -272,7 +295,7 @@ int tb_rows(const fluid_t* h, int W, int rows) {
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, jacobi_tb_kernel<K, false, false>, 32, T::SMEM_LDGSTS);
     if (occ < 1) occ = 1;
     if (h->jacobi_warps_per_sm > 0) occ = std::min(occ, h->jacobi_warps_per_sm);
-    const int resident_warps = h->sm_count * occ;
+    const int resident_warps = std::max(nxw, h->sm_count * occ - reserve);
     const int nch = std::max(1, resident_warps / nxw);
     int r = (rows + nch - 1) / nch;
     r = std::max(r, 4 * K);                 // keep the 2K warm-up rows a bounded fraction
@@ -282,10 +305,12 @@ int tb_rows(const fluid_t* h, int W, int rows) {
     return std::min(r, rows);
 }
 
-int launch_tb_dyn(fluid_t* h, int K, JacobiArgs a, bool scale) {
+// rows_fixed > 0: use that chunk height (the boundary strips of a slab are one chunk each);
+// reserve: resident streams to leave free on the chip (for a launch that runs beside this one)
+int launch_tb_dyn(fluid_t* h, int K, JacobiArgs a, bool scale, int rows_fixed = 0, int reserve = 0) {
     const int rows = a.out_hi - a.out_lo;
     switch (K) {
-#define CASE(KK) case KK: a.rows_per_chunk = tb_rows<KK>(h, a.W, rows); return launch_tb_k<KK>(h, a, scale);
+#define CASE(KK) case KK: a.rows_per_chunk = rows_fixed > 0 ? rows_fixed : tb_rows<KK>(h, a.W, rows, reserve); return launch_tb_k<KK>(h, a, scale);
         CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12)
 #undef CASE
     }
@@ -293,7 +318,7 @@ int launch_tb_dyn(fluid_t* h, int K, JacobiArgs a, bool scale) {
 }
 
 bool tb_eligible(const fluid_t* h) {
-    return (h->cfg.sim_w % 4 == 0) && h->cfg.sim_w >= 16 && h->cfg.sim_h >= 2;
+    return !h->half && (h->cfg.sim_w % 4 == 0) && h->cfg.sim_w >= 16 && h->cfg.sim_h >= 2;
 }
 
 // `iters` sweeps reading pressure.read, result in pressure.read (swaps like S:1265).
@@ -313,6 +338,27 @@ int run_jacobi(fluid_t* h, int iters, bool scale_first, int* launches_out) {
     kb = std::min(kb, KMAX);
     if (h->slab()) kb = std::max(1, std::min(kb, h->G - 1));
     const bool naive = (h->cfg.flags & FLUID_FLAG_NAIVE_JACOBI) || kb == 1;
+    if (h->half) {                                   // fp16 storage: the literal loop, every sweep rounds to fp16 (S:1253-1266)
+        const int n = W * H;
+        if (scale_first) {
+            hs::scale_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>((const hs::h1*)h->pressure.read, (hs::h1*)h->pressure.write, n, h->cfg.pressure);
+            int rc = check_launch(h, "hs::scale_kernel"); if (rc) return rc;
+            swap_p(h); ++nl;
+        }
+        for (int k = 0; k < iters; ++k) {
+            if (W % 8 == 0 && W >= 64) {
+                dim3 b(32, 8), g((W / 8 + 31) / 32, (H + 7) / 8);
+                hs::jacobi8_kernel<<<g, b, 0, h->stream>>>((const hs::h1*)h->pressure.read, (const hs::h1*)h->divergence, (hs::h1*)h->pressure.write, W, H);
+            } else {
+                hs::jacobi_kernel<<<hs_grid(W, H), HS_BLOCK, 0, h->stream>>>((const hs::h1*)h->pressure.read, (const hs::h1*)h->divergence, (hs::h1*)h->pressure.write, W, H);
+            }
+            ++h->jacobi_kernel_launches;
+            int rc = check_launch(h, "hs::jacobi_kernel"); if (rc) return rc;
+            swap_p(h); ++nl;
+        }
+        if (launches_out) *launches_out = nl;
+        return FLUID_OK;
+    }
     if (iters <= 0) {
         if (scale_first) {   // clear pass alone (owned + ghost rows; ghosts are refreshed before use anyway)
             const size_t n = sim_cells(h);
@@ -333,14 +379,27 @@ int run_jacobi(fluid_t* h, int iters, bool scale_first, int* launches_out) {
     // one latency-bound message per launch).  If the ghost zone is too thin for that (iterations
     // raised after creation) fall back to one K-row message per launch.
     const bool deep = h->slab() && (iters + 1 <= h->G) && (iters + 1 <= h->row1 - h->row0);
+    // Overlap (deep + blocked + peer-memory or NCCL alike): the exchange and the two boundary strips
+    // of launch 1 — the only rows of it that read ghost rows — go to a second stream, the interior
+    // rows [row0+K1, row1-K1) of launch 1 run meanwhile on the compute stream.  FLUID_HALO_OVERLAP=0
+    // restores the serial order (exchange, then the whole launch).
+    static const bool overlap_off = getenv("FLUID_HALO_OVERLAP") && !strcmp(getenv("FLUID_HALO_OVERLAP"), "0");
+    const int K1 = base + (extra ? 1 : 0);
+    const bool overlap = deep && blocked && !overlap_off && h->stream2 && (h->row1 - h->row0) >= 2 * K1 + 4 * K1;
     if (h->slab()) {
+        if (overlap) {
+            CU(cudaEventRecord(h->ev_fork, h->stream));
+            CU(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
+            h->active = h->stream2;
+        }
         if (deep) {
             HaloItem it[2] = {{h->pressure.read, (size_t)W * sizeof(float), h->roff, h->row0, h->row1, iters + 1, HB_PRESSURE},
                               {h->divergence, (size_t)W * sizeof(float), h->roff, h->row0, h->row1, iters, HB_DIVERGENCE}};
-            int rc = exchange_many(h, it, 2); if (rc) return rc;
+            int rc = exchange_many(h, it, 2);
             // the neighbours' divergence rows: flag their tiny values like the local producers do
-            if ((rc = scan_tiny(h, std::max(h->row0 - iters, 0), h->row0))) return rc;
-            if ((rc = scan_tiny(h, h->row1, std::min(h->row1 + iters, H)))) return rc;
+            if (!rc) rc = scan_tiny(h, std::max(h->row0 - iters, 0), h->row0);
+            if (!rc) rc = scan_tiny(h, h->row1, std::min(h->row1 + iters, H));
+            if (rc) { h->active = h->stream; return rc; }
         } else {
             const int kmax = base + (extra ? 1 : 0);
             int rc = exchange_rows(h, HB_DIVERGENCE, h->divergence, (size_t)W * sizeof(float), h->roff, h->row0, h->row1, kmax);
@@ -369,7 +428,25 @@ int run_jacobi(fluid_t* h, int iters, bool scale_first, int* launches_out) {
         }
         const bool sc = scale_first && k == 0;
         int rc;
-        if (blocked) {
+        if (blocked && overlap && k == 0) {
+            // boundary strips [out_lo, row0+K) and [row1-K, out_hi) behind the exchange on stream2 ...
+            const int nxw = (W + 127) / 128 + 8;             // upper bound of the strips' stream count (any K)
+            JacobiArgs bnd = a;
+            bnd.out_lo = a.out_lo; bnd.out_hi = std::min(h->row0 + K, a.out_hi);
+            bnd.seg2_lo = std::max(h->row1 - K, bnd.out_hi); bnd.seg2_hi = a.out_hi;
+            const int strip = std::max(bnd.out_hi - bnd.out_lo, bnd.seg2_hi - bnd.seg2_lo);
+            bnd.nch1 = 1;
+            rc = launch_tb_dyn(h, K, bnd, sc, strip);        // h->active == stream2
+            h->active = h->stream;
+            if (rc) return rc;
+            CU(cudaEventRecord(h->ev_join, h->stream2));
+            // ... the interior meanwhile on the compute stream, sized to leave the strips' slots free
+            JacobiArgs in = a;
+            in.out_lo = bnd.out_hi; in.out_hi = bnd.seg2_lo;
+            rc = launch_tb_dyn(h, K, in, sc, 0, 2 * nxw);
+            if (rc) return rc;
+            CU(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+        } else if (blocked) {
             rc = launch_tb_dyn(h, K, a, sc);
         } else if (tb_eligible(h)) {
             dim3 b(32, 8);
@@ -412,25 +489,30 @@ int alloc_fields(fluid_t* h) {
         h->divergence = (float*)(h->arena + h->off_div); h->curl = (float*)(h->arena + off_curl);
         h->par_v = h->par_p = h->par_dye = 0;
     } else {
-        CU(cudaMalloc(&h->velocity.read, n * sizeof(float2)));
-        CU(cudaMalloc(&h->velocity.write, n * sizeof(float2)));
-        CU(cudaMalloc(&h->dye.read, nd * sizeof(float4)));
-        CU(cudaMalloc(&h->dye.write, nd * sizeof(float4)));
-        CU(cudaMalloc(&h->pressure.read, n * sizeof(float)));
-        CU(cudaMalloc(&h->pressure.write, n * sizeof(float)));
-        CU(cudaMalloc((void**)&h->divergence, n * sizeof(float)));
-        CU(cudaMalloc((void**)&h->curl, n * sizeof(float)));
-        CU(cudaMemsetAsync(h->velocity.read, 0, n * sizeof(float2), h->stream));
-        CU(cudaMemsetAsync(h->velocity.write, 0, n * sizeof(float2), h->stream));
-        CU(cudaMemsetAsync(h->pressure.read, 0, n * sizeof(float), h->stream));
-        CU(cudaMemsetAsync(h->pressure.write, 0, n * sizeof(float), h->stream));
-        CU(cudaMemsetAsync(h->divergence, 0, n * sizeof(float), h->stream));
-        CU(cudaMemsetAsync(h->curl, 0, n * sizeof(float), h->stream));
+        CU(cudaMalloc(&h->velocity.read, n * vbytes(h)));
+        CU(cudaMalloc(&h->velocity.write, n * vbytes(h)));
+        CU(cudaMalloc(&h->dye.read, nd * dbytes(h)));
+        CU(cudaMalloc(&h->dye.write, nd * dbytes(h)));
+        CU(cudaMalloc(&h->pressure.read, n * sbytes(h)));
+        CU(cudaMalloc(&h->pressure.write, n * sbytes(h)));
+        CU(cudaMalloc((void**)&h->divergence, n * sbytes(h)));
+        CU(cudaMalloc((void**)&h->curl, n * sbytes(h)));
+        CU(cudaMemsetAsync(h->velocity.read, 0, n * vbytes(h), h->stream));
+        CU(cudaMemsetAsync(h->velocity.write, 0, n * vbytes(h), h->stream));
+        CU(cudaMemsetAsync(h->pressure.read, 0, n * sbytes(h), h->stream));
+        CU(cudaMemsetAsync(h->pressure.write, 0, n * sbytes(h), h->stream));
+        CU(cudaMemsetAsync(h->divergence, 0, n * sbytes(h), h->stream));
+        CU(cudaMemsetAsync(h->curl, 0, n * sbytes(h), h->stream));
     }
     { int rc = alloc_tiny_map(h); if (rc) return rc; }
     build_tmaps(h);
-    fill_alpha_kernel<<<(unsigned)((nd + 255) / 256), 256, 0, h->stream>>>((float4*)h->dye.read, nd);
-    fill_alpha_kernel<<<(unsigned)((nd + 255) / 256), 256, 0, h->stream>>>((float4*)h->dye.write, nd);
+    if (h->half) {
+        hs::fill_alpha_kernel<<<(unsigned)((nd + 255) / 256), 256, 0, h->stream>>>((hs::h4*)h->dye.read, nd);
+        hs::fill_alpha_kernel<<<(unsigned)((nd + 255) / 256), 256, 0, h->stream>>>((hs::h4*)h->dye.write, nd);
+    } else {
+        fill_alpha_kernel<<<(unsigned)((nd + 255) / 256), 256, 0, h->stream>>>((float4*)h->dye.read, nd);
+        fill_alpha_kernel<<<(unsigned)((nd + 255) / 256), 256, 0, h->stream>>>((float4*)h->dye.write, nd);
+    }
     return check_launch(h, "fill_alpha_kernel", 2);
 }
 
@@ -516,6 +598,11 @@ int create_common(const fluid_config* cfg, int rank, int world, const void* uid,
     h->aspect_d = (cfg->aspect > 0.0f) ? (double)cfg->aspect : (double)cfg->sim_w / (double)cfg->sim_h;
     h->splat_radius_d = (double)cfg->splat_radius;
     h->rank = rank; h->world = world;
+    h->half = (cfg->flags & FLUID_FLAG_HALF_STORAGE) != 0;
+    if (h->half && world > 1) {
+        int rc = fail(nullptr, FLUID_ERR_INVALID, "FLUID_FLAG_HALF_STORAGE is a single-GPU mode");
+        delete h; return rc;
+    }
     const int H = cfg->sim_h, Hd = cfg->dye_h;
     h->row0 = (int)((long long)H * rank / world);  h->row1 = (int)((long long)H * (rank + 1) / world);
     h->drow0 = (int)((long long)Hd * rank / world); h->drow1 = (int)((long long)Hd * (rank + 1) / world);
@@ -540,6 +627,12 @@ int create_common(const fluid_config* cfg, int rank, int world, const void* uid,
     if (const char* e = getenv("FLUID_JACOBI_WARPS")) h->jacobi_warps_per_sm = atoi(e);
     auto body = [&]() -> int {
         CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        h->active = h->stream;
+        if (world > 1) {
+            CU(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+        }
         for (auto& e : h->mark) CU(cudaEventCreate(&e));
         for (auto& e : h->tev) CU(cudaEventCreate(&e));
         CU(cudaMalloc((void**)&h->halo_flag, sizeof(int)));
@@ -693,10 +786,14 @@ void fluid_destroy(fluid_t* h) {
     free_fields(h);
     cudaFree(h->halo_flag);
     cudaFree(h->dt_dev);
+    cudaFree(h->scratch);
     cudaFree(h->frame);
     if (h->comm) { ncdl::api().CommDestroy(h->comm); h->comm = nullptr; }
     for (auto& e : h->mark) if (e) cudaEventDestroy(e);
     for (auto& e : h->tev) if (e) cudaEventDestroy(e);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -750,11 +847,22 @@ int fluid_get_param(fluid_t* h, int key, float* v) {
 // slab); the public fluid_pass_* wrappers are the single-GPU, one-blit-per-call test surface.
 
 static int do_curl(fluid_t* h, Grid g) {
+    if (h->half) {
+        hs::curl_kernel<<<hs_grid(g.W, g.H), HS_BLOCK, 0, h->stream>>>((const hs::h2*)h->velocity.read, (hs::h1*)h->curl, g.W, g.H);
+        return check_launch(h, "hs::curl_kernel");
+    }
     dim3 b(64, 4);
     curl_kernel<<<grid2d(g.W, g.j_hi - g.j_lo, b), b, 0, h->stream>>>((const float2*)h->velocity.read, h->curl, g);
     return check_launch(h, "curl_kernel");
 }
 static int do_vorticity(fluid_t* h, Grid g) {
+    if (h->half) {
+        hs::vorticity_kernel<<<hs_grid(g.W, g.H), HS_BLOCK, 0, h->stream>>>((const hs::h2*)h->velocity.read, (const hs::h1*)h->curl,
+                                                                            (hs::h2*)h->velocity.write, g.W, g.H, h->cfg.curl, h->dt_dev);
+        int rc = check_launch(h, "hs::vorticity_kernel"); if (rc) return rc;
+        swap_v(h);
+        return FLUID_OK;
+    }
     dim3 b(64, 4);
     vorticity_kernel<<<grid2d(g.W, g.j_hi - g.j_lo, b), b, 0, h->stream>>>(
         (const float2*)h->velocity.read, h->curl, (float2*)h->velocity.write, g, h->cfg.curl, h->dt_dev);
@@ -763,32 +871,56 @@ static int do_vorticity(fluid_t* h, Grid g) {
     return FLUID_OK;
 }
 static int do_divergence(fluid_t* h, Grid g) {
+    if (h->half) {
+        hs::divergence_kernel<<<hs_grid(g.W, g.H), HS_BLOCK, 0, h->stream>>>((const hs::h2*)h->velocity.read, (hs::h1*)h->divergence, g.W, g.H);
+        return check_launch(h, "hs::divergence_kernel");
+    }
     dim3 b(64, 4);
     { int rc = clear_tiny_map(h); if (rc) return rc; }
     divergence_kernel<<<grid2d(g.W, g.j_hi - g.j_lo, b), b, 0, h->stream>>>(
         (const float2*)h->velocity.read, h->divergence, g, h->tiny_map);
     return check_launch(h, "divergence_kernel");
 }
-// rows per warp stream of the row-streaming kernels: enough streams to fill the chip (~16 warps per
-// SM), at least `rmin` rows each so that the halo rows a stream re-reads stay a small fraction
-static StreamArgs stream_args(const fluid_t* h, Grid g, int cols_per_window, int rmin) {
+// rows per warp stream of the row-streaming kernels: one full wave of resident warps (`warps_per_sm`
+// from the occupancy calculator), at least `rmin` rows each so that the halo rows a stream re-reads
+// stay a bounded fraction.  Grids too small to give every SM a warp use the tiled kernels instead.
+static StreamArgs stream_args(const fluid_t* h, Grid g, int cols_per_window, int rmin, int warps_per_sm, int round_to) {
     StreamArgs a{};
     a.g = g;
     a.nxw = (g.W + cols_per_window - 1) / cols_per_window;
     const int rows = g.j_hi - g.j_lo;
-    const int chunks = std::max(1, h->sm_count * 16 / a.nxw);
-    a.rows_per_chunk = std::min(std::max((rows + chunks - 1) / chunks, rmin), std::max(rows, 1));
+    const int chunks = std::max(1, h->sm_count * warps_per_sm / a.nxw);
+    int r = std::max((rows + chunks - 1) / chunks, rmin);
+    r = (r + round_to - 1) / round_to * round_to;
+    a.rows_per_chunk = std::min(r, std::max(rows, 1));
     return a;
+}
+static int stream_warps(const StreamArgs& a) {
+    return a.nxw * ((a.g.j_hi - a.g.j_lo + a.rows_per_chunk - 1) / a.rows_per_chunk);
 }
 static bool streaming_ok(const fluid_t* h) {
     return h->cfg.sim_w % 4 == 0 && h->cfg.sim_w >= 8 && !(h->cfg.flags & FLUID_FLAG_TILED_PASSES);
 }
 
+static int do_curl(fluid_t* h, Grid g);
+static int do_vorticity(fluid_t* h, Grid g);
+static int do_divergence(fluid_t* h, Grid g);
 static int do_cvd(fluid_t* h, Grid g) {
+    if (h->half) {                                   // one launch per reference blit (each rounds to fp16)
+        int rc = do_curl(h, g); if (rc) return rc;
+        if ((rc = do_vorticity(h, g))) return rc;
+        return do_divergence(h, g);
+    }
     { int rc = clear_tiny_map(h); if (rc) return rc; }
-    if (streaming_ok(h)) {
-        const StreamArgs a = stream_args(h, g, CVD2_VALID, 32);
-        const int nwarps = a.nxw * ((g.j_hi - g.j_lo + a.rows_per_chunk - 1) / a.rows_per_chunk);
+    static int cvd_occ = 0;
+    if (!cvd_occ) {
+        int blocks = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, cvd_stream_kernel, 32 * CVD2_WARPS, CVD2_SMEM);
+        cvd_occ = std::max(1, blocks) * CVD2_WARPS;
+    }
+    const StreamArgs a = stream_args(h, g, CVD2_VALID, 16, cvd_occ, 1);
+    const int nwarps = stream_warps(a);
+    if (streaming_ok(h) && nwarps >= h->sm_count) {
         cvd_stream_kernel<<<(nwarps + CVD2_WARPS - 1) / CVD2_WARPS, 32 * CVD2_WARPS, CVD2_SMEM, h->stream>>>(
             (const float2*)h->velocity.read, h->curl, (float2*)h->velocity.write, h->divergence, a, h->cfg.curl,
             h->dt_dev, h->tiny_map);
@@ -806,9 +938,16 @@ static int do_cvd(fluid_t* h, Grid g) {
     return FLUID_OK;
 }
 static int do_gradient(fluid_t* h, Grid g) {
-    if (streaming_ok(h)) {
-        const StreamArgs a = stream_args(h, g, 128, 16);
-        const int nwarps = a.nxw * ((g.j_hi - g.j_lo + a.rows_per_chunk - 1) / a.rows_per_chunk);
+    if (h->half) {
+        hs::gradient_kernel<<<hs_grid(g.W, g.H), HS_BLOCK, 0, h->stream>>>((const hs::h1*)h->pressure.read, (const hs::h2*)h->velocity.read,
+                                                                           (hs::h2*)h->velocity.write, g.W, g.H);
+        int rc = check_launch(h, "hs::gradient_kernel"); if (rc) return rc;
+        swap_v(h);
+        return FLUID_OK;
+    }
+    const StreamArgs a = stream_args(h, g, 128, 8, 32, GS_U);
+    const int nwarps = stream_warps(a);
+    if (streaming_ok(h) && nwarps >= h->sm_count) {
         gradient_stream_kernel<<<(nwarps + GS_WARPS - 1) / GS_WARPS, 32 * GS_WARPS, 0, h->stream>>>(
             (const float*)h->pressure.read, (const float2*)h->velocity.read, (float2*)h->velocity.write, a);
         int rc = check_launch(h, "gradient_stream_kernel"); if (rc) return rc;
@@ -827,6 +966,14 @@ static void valid_rows(int r0, int r1, int g, int H, int* lo, int* hi) {
     *lo = std::max(r0 - g, 0); *hi = std::min(r1 + g, H);
 }
 static int do_advect_velocity(fluid_t* h, Grid out) {
+    if (h->half) {
+        hs::advect_kernel<hs::h2, float2><<<hs_grid(out.W, out.H), HS_BLOCK, 0, h->stream>>>(
+            (const hs::h2*)h->velocity.read, out.W, out.H, (const hs::h2*)h->velocity.read, (hs::h2*)h->velocity.write, out.W, out.H,
+            h->dt_dev, h->cfg.velocity_dissipation);
+        int rc = check_launch(h, "hs::advect_kernel"); if (rc) return rc;
+        swap_v(h);
+        return FLUID_OK;
+    }
     dim3 b(64, 4);
     AdvectArgs a{};
     a.vel = sim_grid(h); a.src = out;
@@ -835,7 +982,11 @@ static int do_advect_velocity(fluid_t* h, Grid out) {
     a.dtp = h->dt_dev; a.dissipation = h->cfg.velocity_dissipation; a.halo_violation = h->halo_flag;
     a.tsx = a.dsx = (float)(1.0 / (double)h->cfg.sim_w); a.tsy = a.dsy = (float)(1.0 / (double)h->cfg.sim_h);
     const bool p2 = is_pow2(h->cfg.sim_w) && is_pow2(h->cfg.sim_h);
-    if (p2) advect_velocity_kernel<true><<<grid2d(out.W, out.j_hi - out.j_lo, b), b, 0, h->stream>>>(
+    if (p2 && h->cfg.sim_w >= 128 && !(h->cfg.flags & FLUID_FLAG_TILED_PASSES)) {    // 4 cells per thread, 32 apart
+        dim3 b4(32, 8), g4(out.W / 128, (out.j_hi - out.j_lo + 7) / 8);
+        if (h->slab()) advect_velocity4_kernel<true><<<g4, b4, 0, h->stream>>>((const float2*)h->velocity.read, (float2*)h->velocity.write, a);
+        else advect_velocity4_kernel<false><<<g4, b4, 0, h->stream>>>((const float2*)h->velocity.read, (float2*)h->velocity.write, a);
+    } else if (p2) advect_velocity_kernel<true><<<grid2d(out.W, out.j_hi - out.j_lo, b), b, 0, h->stream>>>(
         (const float2*)h->velocity.read, (float2*)h->velocity.write, a);
     else advect_velocity_kernel<false><<<grid2d(out.W, out.j_hi - out.j_lo, b), b, 0, h->stream>>>(
         (const float2*)h->velocity.read, (float2*)h->velocity.write, a);
@@ -844,6 +995,14 @@ static int do_advect_velocity(fluid_t* h, Grid out) {
     return FLUID_OK;
 }
 static int do_advect_dye(fluid_t* h) {
+    if (h->half) {
+        hs::advect_kernel<hs::h4, float4><<<hs_grid(h->cfg.dye_w, h->cfg.dye_h), HS_BLOCK, 0, h->stream>>>(
+            (const hs::h2*)h->velocity.read, h->cfg.sim_w, h->cfg.sim_h, (const hs::h4*)h->dye.read, (hs::h4*)h->dye.write,
+            h->cfg.dye_w, h->cfg.dye_h, h->dt_dev, h->cfg.density_dissipation);
+        int rc = check_launch(h, "hs::advect_kernel"); if (rc) return rc;
+        swap_dye(h);
+        return FLUID_OK;
+    }
     dim3 b(64, 4);
     AdvectArgs a{};
     a.vel = sim_grid(h); a.src = dye_grid(h);
@@ -857,7 +1016,13 @@ static int do_advect_dye(fluid_t* h) {
     const bool same = h->cfg.sim_w == h->cfg.dye_w && h->cfg.sim_h == h->cfg.dye_h;
     const dim3 gr = grid2d(a.src.W, a.src.j_hi - a.src.j_lo, b);
     const float2* V = (const float2*)h->velocity.read; const float4* Dr = (const float4*)h->dye.read; float4* Dw = (float4*)h->dye.write;
-    if (p2 && same) advect_dye_kernel<true, true><<<gr, b, 0, h->stream>>>(V, Dr, Dw, a);
+    if (p2 && a.src.W >= 128 && !(h->cfg.flags & FLUID_FLAG_TILED_PASSES)) {         // 4 cells per thread, 32 apart
+        dim3 b4(32, 8), g4(a.src.W / 128, (a.src.j_hi - a.src.j_lo + 7) / 8);
+        if (same && h->slab()) advect_dye4_kernel<true, true><<<g4, b4, 0, h->stream>>>(V, Dr, Dw, a);
+        else if (same) advect_dye4_kernel<true, false><<<g4, b4, 0, h->stream>>>(V, Dr, Dw, a);
+        else if (h->slab()) advect_dye4_kernel<false, true><<<g4, b4, 0, h->stream>>>(V, Dr, Dw, a);
+        else advect_dye4_kernel<false, false><<<g4, b4, 0, h->stream>>>(V, Dr, Dw, a);
+    } else if (p2 && same) advect_dye_kernel<true, true><<<gr, b, 0, h->stream>>>(V, Dr, Dw, a);
     else if (p2) advect_dye_kernel<true, false><<<gr, b, 0, h->stream>>>(V, Dr, Dw, a);
     else advect_dye_kernel<false, false><<<gr, b, 0, h->stream>>>(V, Dr, Dw, a);
     int rc = check_launch(h, "advect_dye_kernel"); if (rc) return rc;
@@ -1022,6 +1187,18 @@ int fluid_splat(fluid_t* h, float x, float y, float dx, float dy, float r, float
     double rad = h->splat_radius_d / 100.0;
     if (h->aspect_d > 1.0) rad *= h->aspect_d;
     const float radius = (float)rad;
+    if (h->half) {
+        const int W = h->cfg.sim_w, H = h->cfg.sim_h, Wd = h->cfg.dye_w, Hd = h->cfg.dye_h;
+        hs::splat_velocity_kernel<<<hs_grid(W, H), HS_BLOCK, 0, h->stream>>>((const hs::h2*)h->velocity.read, (hs::h2*)h->velocity.write, W, H,
+                                                                             h->cfg.aspect, x, y, dx, dy, radius);
+        int rc = check_launch(h, "hs::splat_velocity_kernel"); if (rc) return rc;
+        swap_v(h);
+        hs::splat_dye_kernel<<<hs_grid(Wd, Hd), HS_BLOCK, 0, h->stream>>>((const hs::h4*)h->dye.read, (hs::h4*)h->dye.write, Wd, Hd,
+                                                                          h->cfg.aspect, x, y, r, g, b, radius);
+        rc = check_launch(h, "hs::splat_dye_kernel"); if (rc) return rc;
+        swap_dye(h);
+        return FLUID_OK;
+    }
     dim3 bl(64, 4);
     // a splat is point-wise, so the +-3 velocity ghost rows are simply splatted as well
     Grid gs = sim_grid_ext(h, h->slab() ? 3 : 0), gd = dye_grid(h);
@@ -1049,6 +1226,42 @@ int fluid_resize(fluid_t* h, int sim_w, int sim_h, int dye_w, int dye_h) {
     if (h->slab()) return not_on_slab(h, "fluid_resize");
     CU(cudaStreamSynchronize(h->stream));
     drop_graphs(h);                                          // graphs hold the old buffers' addresses
+    if (h->half) {
+        // fp16 storage: widen the old texture, draw the copy through the LINEAR sampler in fp32, round the
+        // new texture to fp16 (what the reference's blit into an RGBA16F / RG16F target does)
+        auto redo = [&](Pair& f, int ow_, int oh_, int nw_, int nh_, int ch, bool alpha) -> int {
+            const size_t on = (size_t)ow_ * oh_ * ch, nn = (size_t)nw_ * nh_ * ch;
+            float *wide = nullptr, *res = nullptr; void *nr = nullptr, *nwp = nullptr;
+            CU(cudaMalloc((void**)&wide, on * 4)); CU(cudaMalloc((void**)&res, nn * 4));
+            CU(cudaMalloc(&nr, nn * 2)); CU(cudaMalloc(&nwp, nn * 2));
+            hs::widen_kernel<<<(unsigned)((on + 255) / 256), 256, 0, h->stream>>>((const hs::h1*)f.read, wide, on);
+            dim3 b(64, 4);
+            if (ch == 4) resample_kernel<float4><<<grid2d(nw_, nh_, b), b, 0, h->stream>>>((const float4*)wide, ow_, oh_, (float4*)res, nw_, nh_);
+            else resample_kernel<float2><<<grid2d(nw_, nh_, b), b, 0, h->stream>>>((const float2*)wide, ow_, oh_, (float2*)res, nw_, nh_);
+            hs::narrow_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, h->stream>>>(res, (hs::h1*)nr, nn);
+            if (alpha) hs::fill_alpha_kernel<<<(unsigned)((nn / 4 + 255) / 256), 256, 0, h->stream>>>((hs::h4*)nwp, nn / 4);
+            else CU(cudaMemsetAsync(nwp, 0, nn * 2, h->stream));
+            int rc = check_launch(h, "half resize", 3); if (rc) return rc;
+            CU(cudaStreamSynchronize(h->stream));
+            cudaFree(wide); cudaFree(res); cudaFree(f.read); cudaFree(f.write);
+            f.read = nr; f.write = nwp;
+            return FLUID_OK;
+        };
+        const int ow = h->cfg.sim_w, oh = h->cfg.sim_h, odw = h->cfg.dye_w, odh = h->cfg.dye_h;
+        int rc;
+        if ((dye_w != odw || dye_h != odh) && (rc = redo(h->dye, odw, odh, dye_w, dye_h, 4, true))) return rc;
+        if ((sim_w != ow || sim_h != oh) && (rc = redo(h->velocity, ow, oh, sim_w, sim_h, 2, false))) return rc;
+        const size_t n = (size_t)sim_w * sim_h;
+        cudaFree(h->pressure.read); cudaFree(h->pressure.write); cudaFree(h->divergence); cudaFree(h->curl);
+        h->pressure = Pair{}; h->divergence = h->curl = nullptr;
+        CU(cudaMalloc(&h->pressure.read, n * 2)); CU(cudaMalloc(&h->pressure.write, n * 2));
+        CU(cudaMalloc((void**)&h->divergence, n * 2)); CU(cudaMalloc((void**)&h->curl, n * 2));
+        CU(cudaMemsetAsync(h->pressure.read, 0, n * 2, h->stream)); CU(cudaMemsetAsync(h->pressure.write, 0, n * 2, h->stream));
+        CU(cudaMemsetAsync(h->divergence, 0, n * 2, h->stream)); CU(cudaMemsetAsync(h->curl, 0, n * 2, h->stream));
+        h->cfg.sim_w = sim_w; h->cfg.sim_h = sim_h; h->cfg.dye_w = dye_w; h->cfg.dye_h = dye_h;
+        h->row0 = 0; h->row1 = sim_h; h->drow0 = 0; h->drow1 = dye_h;
+        return alloc_tiny_map(h);
+    }
     const int ow = h->cfg.sim_w, oh = h->cfg.sim_h, odw = h->cfg.dye_w, odh = h->cfg.dye_h;
     dim3 b(64, 4);
     const size_t n = (size_t)sim_w * sim_h, nd = (size_t)dye_w * dye_h;
@@ -1115,6 +1328,12 @@ int fluid_read(fluid_t* h, int field, float* host, size_t n_floats) {
     if (!h || !host || field_info(h, field, &p, &w, &rows, &ch)) return fail(h, FLUID_ERR_INVALID, "bad field %d", field);
     const size_t n = (size_t)w * rows * ch;
     if (n_floats != n) return fail(h, FLUID_ERR_INVALID, "field %d has %zu floats, caller passed %zu", field, n, n_floats);
+    if (h->half) {                                   // the ABI speaks fp32: widen on the device, then copy
+        int rc = need_scratch(h, n); if (rc) return rc;
+        hs::widen_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>((const hs::h1*)p, h->scratch, n);
+        if ((rc = check_launch(h, "hs::widen_kernel"))) return rc;
+        p = h->scratch;
+    }
     CU(cudaMemcpyAsync(host, p, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return check_halo(h);
@@ -1125,6 +1344,14 @@ int fluid_write(fluid_t* h, int field, const float* host, size_t n_floats) {
     if (!h || !host || field_info(h, field, &p, &w, &rows, &ch)) return fail(h, FLUID_ERR_INVALID, "bad field %d", field);
     const size_t n = (size_t)w * rows * ch;
     if (n_floats != n) return fail(h, FLUID_ERR_INVALID, "field %d has %zu floats, caller passed %zu", field, n, n_floats);
+    if (h->half) {                                   // narrow with round-to-nearest-even, like a texture upload would
+        int rc = need_scratch(h, n); if (rc) return rc;
+        CU(cudaMemcpyAsync(h->scratch, host, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        hs::narrow_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->scratch, (hs::h1*)p, n);
+        if ((rc = check_launch(h, "hs::narrow_kernel"))) return rc;
+        CU(cudaStreamSynchronize(h->stream));
+        return FLUID_OK;
+    }
     CU(cudaMemcpyAsync(p, host, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     if (field == FLUID_FIELD_VELOCITY) h->v_ghost_valid = false;   // ghosts rebuilt by the next step
@@ -1137,6 +1364,13 @@ int fluid_write(fluid_t* h, int field, const float* host, size_t n_floats) {
 
 int fluid_pressure_solve_host(fluid_t* h, const float* div_host, float* p_host, int iters) {
     if (!h || !div_host || !p_host || iters < 0) return fail(h, FLUID_ERR_INVALID, "bad argument");
+    if (h->half) {
+        int rc = fluid_write(h, FLUID_FIELD_DIVERGENCE, div_host, (size_t)h->cfg.sim_w * h->cfg.sim_h);
+        if (!rc) rc = fluid_write(h, FLUID_FIELD_PRESSURE, p_host, (size_t)h->cfg.sim_w * h->cfg.sim_h);
+        if (!rc) rc = run_jacobi(h, iters, true, nullptr);
+        if (!rc) rc = fluid_read(h, FLUID_FIELD_PRESSURE, p_host, (size_t)h->cfg.sim_w * h->cfg.sim_h);
+        return rc;
+    }
     const size_t n = (size_t)h->cfg.sim_w * (h->row1 - h->row0);   // owned rows
     const size_t go = (size_t)h->G * h->cfg.sim_w;
     // Host buffers may be pageable; pinned ones (cudaHostAlloc / cudaHostRegister by the caller)
@@ -1165,8 +1399,16 @@ int fluid_render(fluid_t* h, int width, int height, int shading, float back_r, f
         CU(cudaMalloc((void**)&h->frame, cells * sizeof(float4)));
         h->frame_cells = cells;
     }
+    const float4* dye_src = (const float4*)h->dye.read;
+    if (h->half) {                                   // the sampler widens fp16 texels exactly; shading is fp32 as in the shader
+        const size_t nd = (size_t)h->cfg.dye_w * h->cfg.dye_h * 4;
+        int rc = need_scratch(h, nd); if (rc) return rc;
+        hs::widen_kernel<<<(unsigned)((nd + 255) / 256), 256, 0, h->stream>>>((const hs::h1*)h->dye.read, h->scratch, nd);
+        if ((rc = check_launch(h, "hs::widen_kernel"))) return rc;
+        dye_src = (const float4*)h->scratch;
+    }
     dim3 b(32, 8);
-    display_kernel<<<grid2d(width, height, b), b, 0, h->stream>>>((const float4*)h->dye.read, h->cfg.dye_w, h->cfg.dye_h,
+    display_kernel<<<grid2d(width, height, b), b, 0, h->stream>>>(dye_src, h->cfg.dye_w, h->cfg.dye_h,
                                                                 h->frame, width, height, shading, back_r, back_g, back_b,
                                                                 make_float2((float)(1.0 / (double)width), (float)(1.0 / (double)height)));
     int rc = check_launch(h, "display_kernel"); if (rc) return rc;
@@ -1185,6 +1427,7 @@ int fluid_render_postfx(fluid_t* h, int width, int height, const fluid_postfx* f
     if (!h || !fx || !dither_rgb || !host_rgba || width < 1 || height < 1 || dw < 1 || dh < 1)
         return fail(h, FLUID_ERR_INVALID, "bad argument");
     if (h->slab()) return not_on_slab(h, "fluid_render_postfx");
+    if (h->half) return fail(h, FLUID_ERR_INVALID, "fluid_render_postfx is not built for FLUID_FLAG_HALF_STORAGE (the reference's bloom / sunrays FBOs are fp16 too)");
     const size_t cells = (size_t)width * height;
     if (n_floats != 4 * cells) return fail(h, FLUID_ERR_INVALID, "render target has %zu floats, caller passed %zu", 4 * cells, n_floats);
     int bw, bh, sw, sh;

@@ -132,9 +132,9 @@ int exchange_p2p(fluid_t* h, const HaloItem* it, int count) {
         }
     }
     const unsigned blocks = (unsigned)std::min<unsigned long long>(std::max<unsigned long long>((total4 + 255) / 256, 1), (unsigned long long)h->sm_count * 2);
-    halo_push_kernel<<<blocks, 256, 0, h->stream>>>(pa);
+    halo_push_kernel<<<blocks, 256, 0, h->active>>>(pa);
     int rc = check_launch(h, "halo_push_kernel"); if (rc) return rc;
-    halo_wait_kernel<<<1, 1, 0, h->stream>>>(pa.my_flags, pa.present[0], pa.present[1], pa.seq, pa.err, pa.dbg);
+    halo_wait_kernel<<<1, 1, 0, h->active>>>(pa.my_flags, pa.present[0], pa.present[1], pa.seq, pa.err, pa.dbg);
     rc = check_launch(h, "halo_wait_kernel"); if (rc) return rc;
     h->halo_kernel_launches += 2;
     ++h->halo_groups;
@@ -159,12 +159,12 @@ int exchange_many(fluid_t* h, const HaloItem* it, int count) {
         auto at = [&](int grow) { return b + (size_t)(grow - q.off) * q.row_bytes; };
         const size_t bytes = (size_t)q.n * q.row_bytes;
         if (h->rank + 1 < h->world) {
-            if (!rc) rc = N.Send(at(q.r1 - q.n), bytes, ncdl::ncclInt8, h->rank + 1, h->comm, h->stream);
-            if (!rc) rc = N.Recv(at(q.r1), bytes, ncdl::ncclInt8, h->rank + 1, h->comm, h->stream);
+            if (!rc) rc = N.Send(at(q.r1 - q.n), bytes, ncdl::ncclInt8, h->rank + 1, h->comm, h->active);
+            if (!rc) rc = N.Recv(at(q.r1), bytes, ncdl::ncclInt8, h->rank + 1, h->comm, h->active);
         }
         if (h->rank > 0) {
-            if (!rc) rc = N.Send(at(q.r0), bytes, ncdl::ncclInt8, h->rank - 1, h->comm, h->stream);
-            if (!rc) rc = N.Recv(at(q.r0 - q.n), bytes, ncdl::ncclInt8, h->rank - 1, h->comm, h->stream);
+            if (!rc) rc = N.Send(at(q.r0), bytes, ncdl::ncclInt8, h->rank - 1, h->comm, h->active);
+            if (!rc) rc = N.Recv(at(q.r0 - q.n), bytes, ncdl::ncclInt8, h->rank - 1, h->comm, h->active);
         }
     }
     const int rc2 = N.GroupEnd();

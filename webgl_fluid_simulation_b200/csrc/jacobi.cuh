@@ -44,6 +44,10 @@ struct JacobiArgs {
     float scale;         // SCALE: value of config.PRESSURE
     int* err;            // device error word (3 = a bounded mbarrier wait gave up)
     const unsigned char* tiny_map;   // tb kernel: where divergence defeats the fma contraction (may be null)
+    // tb kernel, optional SECOND row range of the same launch (the two boundary strips of a slab, which
+    // wait for the halo while the interior runs): chunks 0..nch1-1 tile [out_lo, out_hi), the rest
+    // tile [seg2_lo, seg2_hi).  nch1 <= 0: single range.
+    int nch1, seg2_lo, seg2_hi;
 };
 
 // the two tensor maps a temporally blocked launch reads through (TMA staging); 64-byte aligned
@@ -304,57 +308,74 @@ __device__ __forceinline__ void tb_block(float4 (&w)[K][3], float4 (&dr)[TB<K>::
         mbar_wait(tm.bars + st.stg, st.phase, tm.err);
         srow = ring + st.stg * T::STAGE4;
     }
+    // The K levels x 3 steps of a block form a dependency lattice: node (ph, t) needs node
+    // (ph, t-1) of the same step (the fresh row above) and rows of level t-1 from the two previous
+    // steps.  Source order is step by step; ptxas interleaves the chains itself.  (Emitting the
+    // lattice anti-diagonal by anti-diagonal — FLUID_TB_DIAG, legal because ph ascends inside a
+    // diagonal — was measured 3 % SLOWER on B200: profiles/r02_jacobi_layout.md.)
+#ifdef FLUID_TB_DIAG
+#pragma unroll
+    for (int dg = 0; dg < K + 3; ++dg) {
+#pragma unroll
+        for (int ph = 0; ph < 3; ++ph) {
+            const int t = dg - ph;
+            if (t < 0 || t > K) continue;
+#else
 #pragma unroll
     for (int ph = 0; ph < 3; ++ph) {
-        // ---- level 0: the oldest staged row ---------------------------------------------------------
-        float4 in, dv;
-        if (TMA) {
-            in = lds128(srow + ph * 32);
-            dv = lds128(srow + (3 + ph) * 32);
-        } else {
-            cp_async_wait<T::D - 1>();
-            in = lds128(st.stage);
-            dv = lds128(st.stage + T::D * 32);
-            cp_async16(const_cast<float4*>(st.stage), st.pl);
-            cp_async16(const_cast<float4*>(st.stage) + T::D * 32, st.dl);
-            cp_async_commit();
-            if (st.rload < ye) { ++st.rload; st.pl += W4; st.dl += W4; }   // loads clamp to row ye
-            st.slot = (st.slot + 1 == T::D) ? 0 : st.slot + 1;
-            st.stage = ring + st.slot * 32;
-        }
-        if (REV) { in = rev4(in, rev); dv = rev4(dv, rev); }
-        if (SCALE) {
-            in.x = scale * in.x; in.y = scale * in.y; in.z = scale * in.z; in.w = scale * in.w;
-        }
-        if (!EXACT) {                             // d' = -0.25 * d, exact outside the flagged cells
-            const u64 nq = pack2(-0.25f, -0.25f);
-            u64 a = mul2(pack2(dv.x, dv.y), nq), b = mul2(pack2(dv.z, dv.w), nq);
-            unpack2(a, dv.x, dv.y); unpack2(b, dv.z, dv.w);
-        }
-        w[0][(ph + 2) % 3] = in;
-        dr[K + ph] = dv;
-        // ---- levels 1..K ------------------------------------------------------------------------
 #pragma unroll
-        for (int t = 1; t <= K; ++t) {
-            const float4 c = w[t - 1][(ph + 1) % 3];
-            float4 below = w[t - 1][(ph + 0) % 3];
-            float4 above = w[t - 1][(ph + 2) % 3];
-            if (EDGE) {                           // warp-uniform conditions
-                const int r = st.rout + (K - t);  // row produced by level t at this step
-                if (r == 0) below = c;            // CLAMP_TO_EDGE: p[i,-1] = p[i,0]
-                if (r == H - 1) above = c;        //                p[i,H]  = p[i,H-1]
-            }
-            const float4 d = dr[K + ph - t];      // div row staged t steps ago
-            const float4 o = jacobi4<EXACT>(below, c, above, d);
-            if (t < K) {
-                w[t][(ph + 2) % 3] = o;
-            } else if (lane_out && (unsigned)(st.rout - y0) < (unsigned)(y1 - y0)) {
-                *st.op = o;
+        for (int t = 0; t <= K; ++t) {
+#endif
+            if (t == 0) {
+                // ---- level 0: the oldest staged row ---------------------------------------------------
+                float4 in, dv;
+                if (TMA) {
+                    in = lds128(srow + ph * 32);
+                    dv = lds128(srow + (3 + ph) * 32);
+                } else {
+                    cp_async_wait<T::D - 1>();
+                    in = lds128(st.stage);
+                    dv = lds128(st.stage + T::D * 32);
+                    cp_async16(const_cast<float4*>(st.stage), st.pl);
+                    cp_async16(const_cast<float4*>(st.stage) + T::D * 32, st.dl);
+                    cp_async_commit();
+                    if (st.rload < ye) { ++st.rload; st.pl += W4; st.dl += W4; }   // loads clamp to row ye
+                    st.slot = (st.slot + 1 == T::D) ? 0 : st.slot + 1;
+                    st.stage = ring + st.slot * 32;
+                }
+                if (REV) { in = rev4(in, rev); dv = rev4(dv, rev); }
+                if (SCALE) {
+                    in.x = scale * in.x; in.y = scale * in.y; in.z = scale * in.z; in.w = scale * in.w;
+                }
+                if (!EXACT) {                     // d' = -0.25 * d, exact outside the flagged cells
+                    const u64 nq = pack2(-0.25f, -0.25f);
+                    u64 a = mul2(pack2(dv.x, dv.y), nq), b = mul2(pack2(dv.z, dv.w), nq);
+                    unpack2(a, dv.x, dv.y); unpack2(b, dv.z, dv.w);
+                }
+                w[0][(ph + 2) % 3] = in;
+                dr[K + ph] = dv;
+            } else {
+                // ---- level t of step ph ---------------------------------------------------------------
+                const float4 c = w[t - 1][(ph + 1) % 3];
+                float4 below = w[t - 1][(ph + 0) % 3];
+                float4 above = w[t - 1][(ph + 2) % 3];
+                if (EDGE) {                       // warp-uniform conditions
+                    const int r = st.rout + ph + (K - t);   // row produced by level t at this step
+                    if (r == 0) below = c;        // CLAMP_TO_EDGE: p[i,-1] = p[i,0]
+                    if (r == H - 1) above = c;    //                p[i,H]  = p[i,H-1]
+                }
+                const float4 d = dr[K + ph - t];  // div row staged t steps ago
+                const float4 o = jacobi4<EXACT>(below, c, above, d);
+                if (t < K) {
+                    w[t][(ph + 2) % 3] = o;
+                } else if (lane_out && (unsigned)(st.rout + ph - y0) < (unsigned)(y1 - y0)) {
+                    st.op[ph * W4] = o;
+                }
             }
         }
-        ++st.rout;
-        st.op += W4;
     }
+    st.rout += 3;
+    st.op += 3 * W4;
 #pragma unroll
     for (int j = 0; j < K; ++j) dr[j] = dr[j + 3];
     if (TMA) {
@@ -471,20 +492,42 @@ __device__ __forceinline__ void tb_stream(const JacobiArgs& a, const void* tm_p,
     }
 }
 
+#ifdef FLUID_TB_EXACT_INLINE
+#define FLUID_TB_EXACT_ATTR __forceinline__
+#else
+#define FLUID_TB_EXACT_ATTR __noinline__
+#endif
+template <int K, bool SCALE, bool TMA>
+__device__ FLUID_TB_EXACT_ATTR void tb_stream_exact(const JacobiArgs& a, const void* tm_p, const void* tm_d,
+                                             float4* __restrict__ smem4, const int lane, const int x0,
+                                             const int lc, const int gx, const bool rev, const bool lane_out,
+                                             const int y0, const int y1, const int ys, const int ye,
+                                             const bool any_rev) {
+    if (any_rev) tb_stream<K, SCALE, true, true, TMA>(a, tm_p, tm_d, smem4, lane, x0, lc, gx, rev, lane_out, y0, y1, ys, ye);
+    else tb_stream<K, SCALE, false, true, TMA>(a, tm_p, tm_d, smem4, lane, x0, lc, gx, rev, lane_out, y0, y1, ys, ye);
+}
+
 // One warp per CTA: every quantity that steers control flow derives from blockIdx and kernel
 // arguments only, so the compiler can prove the warp converged at each shuffle (no WARPSYNC /
 // BSSY scaffolding) and keeps loop state in uniform registers.
 #ifndef FLUID_TB_MINBLOCKS
 #define FLUID_TB_MINBLOCKS 1     // tuning builds: resident CTAs per SM the register allocation must allow
 #endif
+#ifdef FLUID_TB_MAXNREG            // tuning builds: cap registers directly (192 -> 10 one-warp CTAs per SM)
+#define FLUID_TB_BOUNDS __maxnreg__(FLUID_TB_MAXNREG)
+#else
+#define FLUID_TB_BOUNDS __launch_bounds__(32, FLUID_TB_MINBLOCKS)
+#endif
 template <int K, bool SCALE, bool TMA>
-__global__ void __launch_bounds__(32, FLUID_TB_MINBLOCKS) jacobi_tb_kernel(JacobiArgs a, const __grid_constant__ TmapPair maps) {
+__global__ void FLUID_TB_BOUNDS jacobi_tb_kernel(JacobiArgs a, const __grid_constant__ TmapPair maps) {
     using T = TB<K>;
     extern __shared__ __align__(128) float4 smem4[];
     const int lane = threadIdx.x;
     const int nxw = (a.W + T::VALID - 1) / T::VALID;
     const int wid = blockIdx.x;
-    const int wx = wid % nxw, cy = wid / nxw;
+    const int wx = wid % nxw;
+    int cy = wid / nxw, seg_lo = a.out_lo, seg_hi = a.out_hi;
+    if (a.nch1 > 0 && cy >= a.nch1) { cy -= a.nch1; seg_lo = a.seg2_lo; seg_hi = a.seg2_hi; }
 
     // ---- x geometry of this lane: mirrored / clamped float4 column group ------------------------
     const int W = a.W, H = a.H;
@@ -499,8 +542,8 @@ __global__ void __launch_bounds__(32, FLUID_TB_MINBLOCKS) jacobi_tb_kernel(Jacob
     const int x0 = wx * T::VALID - T::HX;
 
     // ---- y geometry of this warp's stream ----------------------------------------------------------
-    const int y0 = a.out_lo + cy * a.rows_per_chunk;
-    const int y1 = min(y0 + a.rows_per_chunk, a.out_hi);
+    const int y0 = seg_lo + cy * a.rows_per_chunk;
+    const int y1 = min(y0 + a.rows_per_chunk, seg_hi);
     const int ys = max(y0 - K, 0);                    // first input row
     const int ye = min(y1 - 1 + K, H - 1);            // last input row
 
@@ -519,12 +562,14 @@ __global__ void __launch_bounds__(32, FLUID_TB_MINBLOCKS) jacobi_tb_kernel(Jacob
 #endif
     const void* tp = &maps.p;
     const void* td = &maps.d;
-    if (exact) {
-        if (any_rev) tb_stream<K, SCALE, true, true, TMA>(a, tp, td, smem4, lane, x0, lc, gx, rev, lane_out, y0, y1, ys, ye);
-        else tb_stream<K, SCALE, false, true, TMA>(a, tp, td, smem4, lane, x0, lc, gx, rev, lane_out, y0, y1, ys, ye);
+    // The common case first, so that it is laid out first: code placement matters to this kernel (it
+    // runs one or two warps per scheduler, straight out of the instruction caches).  The un-contracted
+    // instantiations are kept out of line for the same reason.
+    if (!exact) {
+        if (!any_rev) tb_stream<K, SCALE, false, false, TMA>(a, tp, td, smem4, lane, x0, lc, gx, rev, lane_out, y0, y1, ys, ye);
+        else tb_stream<K, SCALE, true, false, TMA>(a, tp, td, smem4, lane, x0, lc, gx, rev, lane_out, y0, y1, ys, ye);
     } else {
-        if (any_rev) tb_stream<K, SCALE, true, false, TMA>(a, tp, td, smem4, lane, x0, lc, gx, rev, lane_out, y0, y1, ys, ye);
-        else tb_stream<K, SCALE, false, false, TMA>(a, tp, td, smem4, lane, x0, lc, gx, rev, lane_out, y0, y1, ys, ye);
+        tb_stream_exact<K, SCALE, TMA>(a, tp, td, smem4, lane, x0, lc, gx, rev, lane_out, y0, y1, ys, ye, any_rev);
     }
 }
 

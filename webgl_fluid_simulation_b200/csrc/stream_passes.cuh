@@ -33,6 +33,7 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 // 20 B per cell (read p 4 + v 8, write v 8).  Windows do not overlap: the two lanes at the ends of a
 // warp fetch their one missing neighbour with a scalar load (L1/L2 hit: the next warp streams it).
 constexpr int GS_WARPS = 4;
+constexpr int GS_U = 4;                                          // rows per software-pipeline group
 __global__ void __launch_bounds__(32 * GS_WARPS) gradient_stream_kernel(const float* __restrict__ p,
                                                                        const float2* __restrict__ v,
                                                                        float2* __restrict__ vout, StreamArgs a) {
@@ -52,27 +53,42 @@ __global__ void __launch_bounds__(32 * GS_WARPS) gradient_stream_kernel(const fl
     const float* prow = p + (ptrdiff_t)(0 - a.g.row_off) * W + cc;      // + j*W : row j, this lane's group
     auto P = [&](int j) { return ldg4(prow + (ptrdiff_t)j * W); };
     float4 below = P(max(y0 - 1, 0)), cur = P(y0);
-#pragma unroll 2
-    for (int j = y0; j < y1; ++j) {
-        const float4 above = P(min(j + 1, H - 1));
-        const float4* vr = reinterpret_cast<const float4*>(v + (ptrdiff_t)(j - a.g.row_off) * W + cc);
-        const float4 va = __ldg(vr), vb = __ldg(vr + 1);
-        float l = __shfl_up_sync(0xffffffffu, cur.w, 1);
-        float r = __shfl_down_sync(0xffffffffu, cur.x, 1);
-        if (edge_l) l = __ldg(prow + (ptrdiff_t)j * W - 1);
-        if (edge_r) r = __ldg(prow + (ptrdiff_t)j * W + 4);
-        if (wall_l) l = cur.x;                              // CLAMP_TO_EDGE: p[-1,j] = p[0,j]
-        if (wall_r) r = cur.w;
-        float4 oa, ob;
-        oa.x = va.x - (cur.y - l);        oa.y = va.y - (above.x - below.x);
-        oa.z = va.z - (cur.z - cur.x);    oa.w = va.w - (above.y - below.y);
-        ob.x = vb.x - (cur.w - cur.y);    ob.y = vb.y - (above.z - below.z);
-        ob.z = vb.z - (r - cur.z);        ob.w = vb.w - (above.w - below.w);
-        if (live) {
-            float4* o = reinterpret_cast<float4*>(vout + (ptrdiff_t)(j - a.g.row_off) * W + cc);
-            o[0] = oa; o[1] = ob;
+    // GS_U rows per iteration, every load of the group issued before the first use: 3 x GS_U
+    // 16-byte loads in flight per lane is what keeps HBM busy with this little arithmetic
+#pragma unroll 1
+    for (int j0 = y0; j0 < y1; j0 += GS_U) {
+        float4 ab[GS_U], va[GS_U], vb[GS_U];
+        float el[GS_U], er[GS_U];
+#pragma unroll
+        for (int u = 0; u < GS_U; ++u) {
+            const int j = min(j0 + u, y1 - 1);              // the tail of a chunk re-reads its last row (not stored)
+            ab[u] = P(min(j + 1, H - 1));
+            const float4* vr = reinterpret_cast<const float4*>(v + (ptrdiff_t)(j - a.g.row_off) * W + cc);
+            va[u] = __ldg(vr); vb[u] = __ldg(vr + 1);
+            el[u] = edge_l ? __ldg(prow + (ptrdiff_t)j * W - 1) : 0.f;
+            er[u] = edge_r ? __ldg(prow + (ptrdiff_t)j * W + 4) : 0.f;
         }
-        below = cur; cur = above;
+#pragma unroll
+        for (int u = 0; u < GS_U; ++u) {
+            const int j = j0 + u;
+            const float4 above = ab[u];
+            float l = __shfl_up_sync(0xffffffffu, cur.w, 1);
+            float r = __shfl_down_sync(0xffffffffu, cur.x, 1);
+            if (edge_l) l = el[u];
+            if (edge_r) r = er[u];
+            if (wall_l) l = cur.x;                          // CLAMP_TO_EDGE: p[-1,j] = p[0,j]
+            if (wall_r) r = cur.w;
+            float4 oa, ob;
+            oa.x = va[u].x - (cur.y - l);        oa.y = va[u].y - (above.x - below.x);
+            oa.z = va[u].z - (cur.z - cur.x);    oa.w = va[u].w - (above.y - below.y);
+            ob.x = vb[u].x - (cur.w - cur.y);    ob.y = vb[u].y - (above.z - below.z);
+            ob.z = vb[u].z - (r - cur.z);        ob.w = vb[u].w - (above.w - below.w);
+            if (live && j < y1) {
+                float4* o = reinterpret_cast<float4*>(vout + (ptrdiff_t)(j - a.g.row_off) * W + cc);
+                o[0] = oa; o[1] = ob;
+            }
+            below = cur; cur = above;
+        }
     }
 }
 
@@ -89,6 +105,7 @@ __global__ void __launch_bounds__(32 * GS_WARPS) gradient_stream_kernel(const fl
 // warp produce output, 120 columns.
 constexpr int CVD2_WARPS = 4;
 constexpr int CVD2_VALID = 120;
+constexpr int CVD2_MINBLOCKS = 5;                                // register budget: 5 CTAs = 20 streams per SM
 constexpr int CVD2_RING = 6;                                     // rows in flight per warp (1 KB each)
 constexpr int CVD2_SMEM = CVD2_WARPS * CVD2_RING * 64 * (int)sizeof(float4);
 
@@ -156,12 +173,29 @@ __device__ __forceinline__ void cvd_step(Vel4 (&V)[3], float (&C)[3][4], Vel4 (&
         const float L[4] = {l, C[MID][0], C[MID][1], C[MID][2]};
         const float R[4] = {C[MID][1], C[MID][2], C[MID][3], r};
         const bool bot = (jn <= 0), top = (jn >= H - 1);    // curl[c(j-1)] / curl[c(j+1)] at the walls
+        VortPre pre[4];
+        bool ok = true;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const float T = top ? C[MID][k] : C[NEW][k];
             const float B = bot ? C[MID][k] : C[OLD][k];
-            const float2 nv = vorticity_apply(make_float2(V[OLD].x[k], V[OLD].y[k]), L[k], R[k], T, B, C[MID][k], curl_k, dt);
-            N[NEW].x[k] = nv.x; N[NEW].y[k] = nv.y;         // slot NEW of N now holds new-velocity row s-2
+            pre[k] = vort_pre(L[k], R[k], T, B);
+            ok &= pre[k].ok;
+        }
+        if (__all_sync(0xffffffffu, ok)) {                  // warp-uniform: the branch-free quotients are exact here
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 nv = vort_post(make_float2(V[OLD].x[k], V[OLD].y[k]), pre[k], C[MID][k], curl_k, dt);
+                N[NEW].x[k] = nv.x; N[NEW].y[k] = nv.y;     // slot NEW of N now holds new-velocity row s-2
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {                   // rare (subnormal / non-finite operands): nvcc's guarded sqrt / divisions
+                const float T = top ? C[MID][k] : C[NEW][k];
+                const float B = bot ? C[MID][k] : C[OLD][k];
+                const float2 nv = vorticity_apply(make_float2(V[OLD].x[k], V[OLD].y[k]), L[k], R[k], T, B, C[MID][k], curl_k, dt);
+                N[NEW].x[k] = nv.x; N[NEW].y[k] = nv.y;
+            }
         }
         if (out_lane && (unsigned)(jn - y0) < (unsigned)(y1 - y0)) {
             st.o_vel[0] = make_float4(N[NEW].x[0], N[NEW].y[0], N[NEW].x[1], N[NEW].y[1]);
@@ -195,7 +229,7 @@ __device__ __forceinline__ void cvd_step(Vel4 (&V)[3], float (&C)[3][4], Vel4 (&
     st.o_curl += W4; st.o_vel += 2 * W4; st.o_div += W4;
 }
 
-__global__ void __launch_bounds__(32 * CVD2_WARPS) cvd_stream_kernel(const float2* __restrict__ v,
+__global__ void __launch_bounds__(32 * CVD2_WARPS, CVD2_MINBLOCKS) cvd_stream_kernel(const float2* __restrict__ v,
                                                                     float* __restrict__ curl,
                                                                     float2* __restrict__ vout,
                                                                     float* __restrict__ div, StreamArgs a,
