@@ -66,7 +66,11 @@ typedef enum fluid_param {
     FLUID_CURL = 4,                 /* S:67 default 30    */
     FLUID_SPLAT_RADIUS = 5,         /* S:68 default 0.25  */
     FLUID_ASPECT = 6,               /* canvas.width/canvas.height, S:1444, S:1457-1462 */
-    FLUID_JACOBI_BLOCK = 7          /* build-only tunable: max temporal-block depth, 1 = naive */
+    FLUID_JACOBI_BLOCK = 7,         /* build-only tunable: max temporal-block depth, 1 = naive */
+    FLUID_BACKGROUND = 8            /* what fluid_render* draws the display over (render(), S:1296-1317):
+                                       0 = drawColor(BACK_COLOR); 1 = drawCheckerboard — config.TRANSPARENT on
+                                       the screen (S:1325-1329, checkerboardShader S:531-547, aspect = ASPECT);
+                                       2 = nothing, blending off — TRANSPARENT into a capture target          */
 } fluid_param;
 
 /* Creation flags */
@@ -222,6 +226,12 @@ int fluid_render_postfx(fluid_t* h, int width, int height, const fluid_postfx* f
 
 int fluid_sync(fluid_t* h);
 int fluid_timing_last(fluid_t* h, fluid_timing* out);
+
+/* Page-locked host memory for the buffers a binding hands to fluid_read / fluid_write /
+ * fluid_pressure_solve_host / fluid_render (DMA without a staging copy).  The N-API shim wraps these in
+ * external ArrayBuffers (readPixels' destination, S:301-307), so it needs no CUDA headers itself. */
+void* fluid_host_alloc(size_t bytes);
+void fluid_host_free(void* p);
 
 /* Device time (ms) between two fluid_mark() calls on the handle's stream; slot is 0 or 1.
  * bench.py uses it because torch.cuda.Event cannot see this library's stream. */

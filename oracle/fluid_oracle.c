@@ -277,8 +277,24 @@ void oracle_resample(const float* src, int Ws, int Hs, float* dst, int Wd, int H
  * (S:1319-1323, colorShader S:521-529) then drawDisplay (S:1331-1348, displayShaderSource
  * S:549-612 with the SHADING keyword when `shading`), blended ONE / ONE_MINUS_SRC_ALPHA (S:1305).
  * dye is sampled through its LINEAR filter at the target's resolution w x h; out is w*h RGBA. */
+/* What drawDisplay is blended over (render(), S:1296-1317): bg_mode 0 = drawColor(BACK_COLOR)
+ * (S:1319-1323); 1 = drawCheckerboard (TRANSPARENT on the screen, S:1325-1329 + checkerboardShader
+ * S:531-547: v = mod(floor(uv.x*25*aspect) + floor(uv.y*25), 2) * 0.1 + 0.8); 2 = nothing and
+ * blending disabled (TRANSPARENT into a capture target): the display colour goes out as it is. */
+static inline void background(int bg_mode, const float* back_rgb, float aspect, float uvx, float uvy, float* bg) {
+    if (bg_mode == 1) {
+        const float x = floorf((uvx * 25.0f) * aspect), y = floorf((uvy * 25.0f) * 1.0f);
+        const float sxy = x + y;
+        float v = sxy - 2.0f * floorf(sxy / 2.0f);                       /* GLSL mod */
+        v = v * 0.1f + 0.8f;
+        bg[0] = bg[1] = bg[2] = v;
+    } else {
+        bg[0] = back_rgb[0]; bg[1] = back_rgb[1]; bg[2] = back_rgb[2];
+    }
+}
+
 void oracle_display(const float* dye, int Wd, int Hd, float* out, int w, int h, int shading,
-                    const float* back_rgb) {
+                    const float* back_rgb, int bg_mode, float aspect) {
     const float tsx = (float)(1.0 / (double)w), tsy = (float)(1.0 / (double)h);   /* S:1337 */
 #pragma omp parallel for schedule(static)
     for (int j = 0; j < h; ++j) {
@@ -306,10 +322,13 @@ void oracle_display(const float* dye, int Wd, int Hd, float* out, int w, int h, 
             }
             const float a = fmaxf(c[0], fmaxf(c[1], c[2]));
             float* o = out + ((size_t)j * w + i) * 4;
+            if (bg_mode == 2) { o[0] = c[0]; o[1] = c[1]; o[2] = c[2]; o[3] = a; continue; }
+            float bg[3];
+            background(bg_mode, back_rgb, aspect, uvx, uvy, bg);
             const float k = 1.0f - a;                                        /* ONE_MINUS_SRC_ALPHA */
-            o[0] = c[0] + back_rgb[0] * k;
-            o[1] = c[1] + back_rgb[1] * k;
-            o[2] = c[2] + back_rgb[2] * k;
+            o[0] = c[0] + bg[0] * k;
+            o[1] = c[1] + bg[1] * k;
+            o[2] = c[2] + bg[2] * k;
             o[3] = a + 1.0f * k;
         }
     }
@@ -445,7 +464,7 @@ void oracle_blur3(const float* src, float* dst, int w, int h, float tsx, float t
 /* displayShaderSource S:549-612 with SHADING + BLOOM + SUNRAYS, over drawColor, premultiplied blend */
 void oracle_display_full(const float* dye, int Wd, int Hd, const float* bloom, int bw, int bh,
                          const float* sun, int sw, int sh, const float* dither, int dw, int dh,
-                         float* out, int w, int h, const float* back_rgb) {
+                         float* out, int w, int h, const float* back_rgb, int bg_mode, float aspect) {
     const float tsx = (float)(1.0 / (double)w), tsy = (float)(1.0 / (double)h);
     const float dsx = (float)((double)w / (double)dw), dsy = (float)((double)h / (double)dh);   /* S:1626-1631 */
 #pragma omp parallel for schedule(static)
@@ -479,9 +498,12 @@ void oracle_display_full(const float* dye, int Wd, int Hd, const float* bloom, i
                 cc[k] = ck + bk;
             }
             a = fmaxf(cc[0], fmaxf(cc[1], cc[2]));
-            const float k1 = 1.0f - a;
             float* o = out + ((size_t)j * w + i) * 4;
-            o[0] = cc[0] + back_rgb[0] * k1; o[1] = cc[1] + back_rgb[1] * k1; o[2] = cc[2] + back_rgb[2] * k1;
+            if (bg_mode == 2) { o[0] = cc[0]; o[1] = cc[1]; o[2] = cc[2]; o[3] = a; continue; }
+            float bg[3];
+            background(bg_mode, back_rgb, aspect, uvx, uvy, bg);
+            const float k1 = 1.0f - a;
+            o[0] = cc[0] + bg[0] * k1; o[1] = cc[1] + bg[1] * k1; o[2] = cc[2] + bg[2] * k1;
             o[3] = a + 1.0f * k1;
         }
     }

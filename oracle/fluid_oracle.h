@@ -49,10 +49,11 @@ void oracle_splat(const float* base, float* out, int W, int H, int C, float aspe
 void oracle_resample(const float* src, int Ws, int Hs, float* dst, int Wd, int Hd, int C);
 
 /* render() without post-FX: drawColor + drawDisplay (S:1296-1348, displayShaderSource S:549-612) */
+/* bg_mode: 0 drawColor(BACK_COLOR), 1 drawCheckerboard (aspect = canvas.width / canvas.height), 2 none / no blend */
 void oracle_display(const float* dye, int Wd, int Hd, float* out, int w, int h, int shading,
-                    const float* back_rgb);
+                    const float* back_rgb, int bg_mode, float aspect);
 
-/* post-FX chain (oracle side only so far): bloom S:614-674 + S:1350-1394, sunrays S:676-724 +
+/* post-FX chain: bloom S:614-674 + S:1350-1394, sunrays S:676-724 +
  * S:1396-1419, full display S:549-612 */
 void oracle_bloom_prefilter(const float* dye, int Wd, int Hd, float* out, int w, int h, float curve0,
                             float curve1, float curve2, float threshold);
@@ -62,7 +63,7 @@ void oracle_sunrays(const float* mask, int Wm, int Hm, float* out, int w, int h,
 void oracle_blur3(const float* src, float* dst, int w, int h, float tsx, float tsy);
 void oracle_display_full(const float* dye, int Wd, int Hd, const float* bloom, int bw, int bh,
                          const float* sun, int sw, int sh, const float* dither, int dw, int dh,
-                         float* out, int w, int h, const float* back_rgb);
+                         float* out, int w, int h, const float* back_rgb, int bg_mode, float aspect);
 
 /* fp16 storage emulation (S:138-147, S:986-1006): round every element through IEEE half, RNE */
 void oracle_round_half(float* a, size_t n);

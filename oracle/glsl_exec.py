@@ -533,16 +533,23 @@ class GLSLSim:
         sp.set(uTarget=self.dye.read, color=tuple(color))
         sp.blit(self.dye.write); self.dye.swap()
 
-    def render(self, width, height, shading=True, back_color=(0, 0, 0)):
-        """render(target) with config.BLOOM = config.SUNRAYS = false, TRANSPARENT = false
-        (S:1296-1317): drawColor(normalizeColor(BACK_COLOR)) then drawDisplay, blended
-        ONE / ONE_MINUS_SRC_ALPHA (S:1305).  Returns the (height, width, 4) float target."""
+    def render(self, width, height, shading=True, back_color=(0, 0, 0), transparent=False, to_screen=True):
+        """render(target) with config.BLOOM = config.SUNRAYS = false (S:1296-1317).  TRANSPARENT false:
+        drawColor(normalizeColor(BACK_COLOR)) then drawDisplay, blended ONE / ONE_MINUS_SRC_ALPHA
+        (S:1305).  TRANSPARENT on the screen (target == null): drawCheckerboard instead of drawColor
+        (S:1311-1312); TRANSPARENT into a capture target: no background, blending disabled (S:1307-1308).
+        Returns the (height, width, 4) float target."""
         js = open(REFERENCE_JS).read()
         target = Texture(width, height, 4, True)
-        color = Program(js, "baseVertexShader", "colorShader")
-        color.set(texelSize=(1.0 / width, 1.0 / height),
-                  color=(back_color[0] / 255, back_color[1] / 255, back_color[2] / 255, 1))   # S:1321, S:1599
-        color.blit(target)
+        if not transparent:
+            color = Program(js, "baseVertexShader", "colorShader")
+            color.set(texelSize=(1.0 / width, 1.0 / height),
+                      color=(back_color[0] / 255, back_color[1] / 255, back_color[2] / 255, 1))   # S:1321, S:1599
+            color.blit(target)
+        elif to_screen:
+            chk = Program(js, "baseVertexShader", "checkerboardShader")
+            chk.set(texelSize=(1.0 / width, 1.0 / height), aspectRatio=width / height)            # S:1327
+            chk.blit(target)
         dst = target.data.copy()
         disp = Program(js, "baseVertexShader", "displayShaderSource", ("SHADING",) if shading else ())
         # the dye texture is sampled through its LINEAR filter here whatever the advection path was
@@ -551,6 +558,8 @@ class GLSLSim:
         disp.set(texelSize=(1.0 / width, 1.0 / height), uTexture=dye)                      # S:1337-1338
         disp.blit(target)
         src = target.data
+        if transparent and not to_screen:
+            return src.astype(F)                                                            # gl.disable(BLEND), S:1308
         one_minus_a = (F(1.0) - src[..., 3:4]).astype(F)
         return (src + dst * one_minus_a).astype(F)                                          # S:1305
 

@@ -49,7 +49,7 @@ def lib():
         L.oracle_splat.argtypes = [_f, _f, i, i, i, f, f, f, _f, f]
         L.oracle_resample.argtypes = [_f, i, i, _f, i, i, i]
         L.oracle_round_half.argtypes = [_f, sz]
-        L.oracle_display.argtypes = [_f, i, i, _f, i, i, i, _f]; L.oracle_display.restype = None
+        L.oracle_display.argtypes = [_f, i, i, _f, i, i, i, _f, i, f]; L.oracle_display.restype = None
         L.oracle_num_threads.restype = i
         for fn in (L.oracle_curl, L.oracle_vorticity, L.oracle_divergence, L.oracle_clear,
                    L.oracle_jacobi, L.oracle_jacobi_iters, L.oracle_gradient_subtract,
@@ -176,27 +176,32 @@ def resample(src, Wd, Hd):
     return out
 
 
-def display(dye, w, h, shading=True, back_rgb=(0.0, 0.0, 0.0)):
-    """render() with bloom / sunrays off: (h, w, 4) float RGBA, row 0 = bottom."""
+BG_COLOR, BG_CHECKERBOARD, BG_NONE = 0, 1, 2   # what drawDisplay is blended over (render(), S:1296-1317)
+
+
+def display(dye, w, h, shading=True, back_rgb=(0.0, 0.0, 0.0), background=BG_COLOR, aspect=None):
+    """render() with bloom / sunrays off: (h, w, 4) float RGBA, row 0 = bottom.  background:
+    BG_COLOR = drawColor(BACK_COLOR); BG_CHECKERBOARD = TRANSPARENT on the screen (S:1325-1329);
+    BG_NONE = TRANSPARENT into a capture target (blending disabled)."""
     dye = _c(dye); Hd, Wd, _ = dye.shape
     out = np.empty((h, w, 4), np.float32)
     back = np.asarray(back_rgb, np.float32)
-    lib().oracle_display(_p(dye), Wd, Hd, _p(out), w, h, 1 if shading else 0, _p(back))
+    lib().oracle_display(_p(dye), Wd, Hd, _p(out), w, h, 1 if shading else 0, _p(back), int(background),
+                         float(w / h if aspect is None else aspect))
     return out
 
 
-def render_postfx(dye, w, h, dither, cfg=None, back_rgb=(0.0, 0.0, 0.0)):
+def render_postfx(dye, w, h, dither, cfg=None, back_rgb=(0.0, 0.0, 0.0), background=0, aspect=None):
     """render(null) with SHADING + BLOOM + SUNRAYS (reference desktop defaults S:70-84): applyBloom
     (S:1350-1394), applySunrays + blur (S:1396-1419), drawColor + drawDisplay (S:1296-1348), FBO
-    sizes from getResolution (S:1012-1043).  ORACLE SIDE ONLY: no CUDA counterpart yet.
-    dither: (dh, dw, 3) float in [0,1], row 0 = first image row (no UNPACK_FLIP_Y)."""
+    sizes from getResolution (S:1012-1043).  dither: (dh, dw, 3) float in [0,1], row 0 = first image row (no UNPACK_FLIP_Y)."""
     L = lib(); i, f = C.c_int, C.c_float
     L.oracle_bloom_prefilter.argtypes = [_f, i, i, _f, i, i, f, f, f, f]
     L.oracle_box4.argtypes = [_f, i, i, _f, i, i, f, i]
     L.oracle_sunrays_mask.argtypes = [_f, _f, i, i]
     L.oracle_sunrays.argtypes = [_f, i, i, _f, i, i, f]
     L.oracle_blur3.argtypes = [_f, _f, i, i, f, f]
-    L.oracle_display_full.argtypes = [_f, i, i, _f, i, i, _f, i, i, _f, i, i, _f, i, i, _f]
+    L.oracle_display_full.argtypes = [_f, i, i, _f, i, i, _f, i, i, _f, i, i, _f, i, i, _f, i, f]
     for fn in (L.oracle_bloom_prefilter, L.oracle_box4, L.oracle_sunrays_mask, L.oracle_sunrays, L.oracle_blur3,
                L.oracle_display_full):
         fn.restype = None
@@ -244,7 +249,7 @@ def render_postfx(dye, w, h, dither, cfg=None, back_rgb=(0.0, 0.0, 0.0)):
     out = np.empty((h, w, 4), np.float32)
     back = np.asarray(back_rgb, np.float32)
     L.oracle_display_full(_p(dye), Wd, Hd, _p(bloom), bw, bh, _p(sun), sw, sh, _p(dither), dither.shape[1],
-                          dither.shape[0], _p(out), w, h, _p(back))
+                          dither.shape[0], _p(out), w, h, _p(back), int(background), float(w / h if aspect is None else aspect))
     return dict(target=out, bloom=bloom, sunrays=sun, mask_alpha=mask[..., 3].copy(), pyramid=pyr)
 
 

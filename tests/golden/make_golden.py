@@ -148,6 +148,14 @@ if __name__ == "__main__":
         resample("resample_v_32_to_48", 32, 32, 48, 48, 2, 31)           # up-sample, ragged ratio
         resample("resample_dye_64_to_32", 64, 64, 32, 32, 4, 32)         # down-sample by 2 (power of two)
         resample("resample_dye_40x28_to_64x48", 40, 28, 64, 48, 4, 33)
+        # TRANSPARENT: checkerboard under the display on the screen, bare display into a capture target
+        rng = np.random.default_rng(41)
+        gs = G.GLSLSim(16, 16, 64, 32)
+        dye = (rng.random((32, 64, 4), dtype=np.float32) ** 3 * 1.5).astype(np.float32); dye[..., 3] = 1
+        gs.load(dye=dye)
+        np.savez_compressed(os.path.join(OUT, "display_transparent_64x32_to_128x64.npz"), in_dye=dye, w=128, h=64,
+                            checker=gs.render(128, 64, True, transparent=True, to_screen=True),
+                            bare=gs.render(128, 64, True, transparent=True, to_screen=False))
         # BASELINE configs[0]: 128x128 sim / 256x256 dye, 20 iterations (the reference's own defaults
         # except the dye size) -- two whole steps after multipleSplats(5)
         scenario("config0_128_256", 128, 128, 256, 256, 5, 2, dict(CURL=30, PRESSURE_ITERATIONS=20), 4321)

@@ -423,11 +423,19 @@ def test_render_display_bitwise_vs_oracle(pkg, oracle, Wd, Hd, w, h):
         assert bits_equal(got, oracle.display(dye, w, h, shading, (30 / 255, 60 / 255, 200 / 255))), shading
     img = s.textureToCanvas(got)
     assert img.dtype == np.uint8 and img.shape == (h, w, 4)
-    s.config["BLOOM"] = True
-    with pytest.raises(NotImplementedError):
-        s.render(w, h)
+    # config.TRANSPARENT: checkerboard under the display on the screen, bare display into a capture target
+    s.config["TRANSPARENT"] = True; s.canvas = {"width": w, "height": h}
+    assert bits_equal(s.render(w, h), oracle.display(dye, w, h, False, background=oracle.BG_CHECKERBOARD))
+    assert bits_equal(s.render(w, h, target=True), oracle.display(dye, w, h, False, background=oracle.BG_NONE))
+    s.config["TRANSPARENT"] = False
+    assert bits_equal(s.render(w, h), got)
     s.close()
     if (Wd, w) == (64, 128):
+        g = golden("display_transparent_64x32_to_128x64")        # executed checkerboardShader + displayShader
+        s = make(pkg, 16, 16, 64, 32); s.canvas = {"width": 128, "height": 64}
+        s.writeField("dye", g["in_dye"]); s.config["TRANSPARENT"] = True
+        assert bits_equal(s.render(128, 64), g["checker"]) and bits_equal(s.render(128, 64, target=True), g["bare"])
+        s.close()
         g = golden("display_64_to_128")
         s = make(pkg, 16, 16, 64, 64)
         s.writeField("dye", g["in_dye"]); s.config["BACK_COLOR"] = {"r": 30, "g": 60, "b": 200}

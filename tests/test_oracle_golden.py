@@ -162,3 +162,11 @@ def test_config0_matches_reference_orchestration(oracle):
         s.step(float(g["dt"]))
         for n in ("velocity", "dye", "pressure", "divergence", "curl"):
             assert max_rel(getattr(s, n), g[f"s{k}_{n}"]) < tol, (k, n)
+
+
+def test_transparent_display_matches_executed_shaders(oracle):
+    """config.TRANSPARENT (S:1303-1312): checkerboardShader under the display on the screen, the bare
+    un-blended display into a capture target -- against the executed reference shaders, bitwise."""
+    g = golden("display_transparent_64x32_to_128x64")
+    assert bits_equal(oracle.display(g["in_dye"], 128, 64, True, background=oracle.BG_CHECKERBOARD), g["checker"])
+    assert bits_equal(oracle.display(g["in_dye"], 128, 64, True, background=oracle.BG_NONE), g["bare"])

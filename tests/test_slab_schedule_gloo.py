@@ -123,10 +123,10 @@ def test_plan_arithmetic():
     assert jacobi_launches(20, 12) == [10, 10] and jacobi_launches(0) == [] and sum(jacobi_launches(37, 9)) == 37
     assert [rows(10, r, 3) for r in range(3)] == [(0, 3), (3, 6), (6, 10)]
     pl = SlabPlan(8192, 8192, 3, 8, iterations=40)
-    assert (pl.row0, pl.row1, pl.G, pl.Gd) == (3072, 4096, 42, 42)
+    assert (pl.row0, pl.row1, pl.G, pl.Gd) == (3072, 4096, 64, 64)
     assert pl.jacobi_messages(40) == [("pressure+divergence", 41)]
     assert pl.launch_extents(40) == [(10, 31), (10, 21), (10, 11), (10, 1)]
-    thin = SlabPlan(8192, 8192, 3, 8, iterations=5)                 # iterations raised after creation
+    thin = SlabPlan(8192, 8192, 3, 8, halo=32, iterations=5)        # iterations raised after creation
     assert thin.G == 32 and not thin.deep(40)
     assert thin.jacobi_messages(40) == [("divergence", 10)] + [("pressure", 10)] * 3 + [("pressure", 11)]
     assert SlabPlan(4096, 4096, 0, 1).jacobi_messages(50) == []

@@ -14,7 +14,7 @@ rng = np.random.default_rng(0)
 if mode == "step":
     s = pkg.FluidSimulation({"SIM_RESOLUTION": W, "DYE_RESOLUTION": W, "PRESSURE_ITERATIONS": 50}, 1024, 1024,
                             random=np.random.RandomState(1234).random_sample)
-    s.multipleSplats(4)
+    s.multipleSplats(16)                       # the same field bench.py's full_step leg times
     for _ in range(3):
         s.step(0.016666)
     s.sync()

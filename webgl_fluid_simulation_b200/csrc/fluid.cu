@@ -53,6 +53,8 @@ struct fluid {
     uint64_t launches = 0;
     uint64_t jacobi_kernel_launches = 0;   // Jacobi kernels only (fluid_stat FLUID_STAT_JACOBI_LAUNCHES)
     uint64_t halo_kernel_launches = 0;     // halo_push / halo_wait kernels of the peer-memory transport
+    bool pdl_chain = false;                // the next blocked Jacobi launch directly follows another one of the same solve
+    bool capturing = false;                // inside the stream capture of a step graph
     bool half = false;                     // FLUID_FLAG_HALF_STORAGE: fields are fp16 (half_passes.cuh), single GPU only
     float* scratch = nullptr;              // half mode: fp32 staging of fluid_read / fluid_write / render
     size_t scratch_floats = 0;
@@ -63,6 +65,7 @@ struct fluid {
     struct Tmaps { CUtensorMap p[2]; void* p_ptr[2] = {nullptr, nullptr}; CUtensorMap d; bool ok = false; } tmaps;
     double splat_radius_d = 0.25;          // config.SPLAT_RADIUS and the canvas aspect as the JS doubles they are
     double aspect_d = 1.0;                 // (correctRadius S:1457-1462 is double arithmetic, narrowed once)
+    int background = 0;                    // FLUID_BACKGROUND: what render() draws the display over (0 colour, 1 checkerboard, 2 none)
     fluid_timing timing{};
     bool have_timing = false;
     std::string err;
@@ -91,6 +94,9 @@ struct fluid {
     } peer[2];                       // [0] = rank-1 (below), [1] = rank+1 (above)
     bool p2p = false;
     uint32_t p2p_seq = 0;
+    // divergence ghost rows of the exchange about to be issued: the peer-memory wait kernel scans them (halo.cuh)
+    struct { const float* div; unsigned char* map; int W, row_off, lo0, hi0, lo1, hi1; } scan{};
+    bool scan_pending = false;
     // ---- step() as a CUDA graph (single GPU): one instantiated graph per (dt, config scalars, parity)
     struct StepGraph { cudaGraphExec_t exec = nullptr; int flip_v = 0, flip_p = 0, flip_dye = 0, kernels = 0, jacobi_launches = 0; };
     std::map<std::string, StepGraph> graphs;
@@ -251,11 +257,13 @@ void build_tmaps(fluid_t* h) {
                   encode_rows_map(&h->tmaps.d, h->divergence, h->cfg.sim_w, rows);
 }
 
-// staging of the blocked kernel: 2-D TMA boxes when tensor maps could be built (FLUID_TB_STAGE=ldgsts
-// selects the per-lane cp.async ring instead)
+// staging of the blocked kernel.  Default: the per-lane cp.async (LDGSTS) ring — measured 4-6 % faster
+// than the 2-D TMA boxes on B200 at 4096^2 x 50 (0.2575 vs 0.2685 ms per solve; the elected-lane issue +
+// mbarrier poll sit in a one-warp CTA's only instruction stream; profiles/r02_jacobi_staging.md).
+// FLUID_TB_STAGE=tma selects the tensor-map path (bit-identical results).
 bool tb_use_tma(const fluid_t* h) {
-    static const bool want_ldgsts = getenv("FLUID_TB_STAGE") && !strcmp(getenv("FLUID_TB_STAGE"), "ldgsts");
-    return h->tmaps.ok && !want_ldgsts;
+    static const bool want_tma = getenv("FLUID_TB_STAGE") && !strcmp(getenv("FLUID_TB_STAGE"), "tma");
+    return h->tmaps.ok && want_tma;
 }
 
 template <int K, bool SCALE>
@@ -266,13 +274,24 @@ int launch_tb(fluid_t* h, const JacobiArgs& a) {
     if (a.nch1 > 0) nch = a.nch1 + (a.seg2_hi - a.seg2_lo + a.rows_per_chunk - 1) / a.rows_per_chunk;
     TmapPair maps;
     memset(&maps, 0, sizeof maps);
+    // chained to the previous launch of the same solve by programmatic dependent launch (jacobi.cuh);
+    // not while a graph is being captured, FLUID_PDL=0 turns it off
+    static const bool pdl_off = getenv("FLUID_PDL") && !strcmp(getenv("FLUID_PDL"), "0");
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(nxw * nch); lc.blockDim = dim3(32); lc.stream = h->active;
+    lc.attrs = attr; lc.numAttrs = (h->pdl_chain && !pdl_off && !h->capturing) ? 1 : 0;
     if (tb_use_tma(h)) {
         const int k = (a.pin == h->tmaps.p_ptr[0]) ? 0 : 1;
         memcpy(maps.p, &h->tmaps.p[k], sizeof(CUtensorMap));
         memcpy(maps.d, &h->tmaps.d, sizeof(CUtensorMap));
-        jacobi_tb_kernel<K, SCALE, true><<<nxw * nch, 32, T::SMEM_TMA, h->active>>>(a, maps);   // one warp per CTA
+        lc.dynamicSmemBytes = T::SMEM_TMA;
+        cudaLaunchKernelEx(&lc, jacobi_tb_kernel<K, SCALE, true>, a, maps);                       // one warp per CTA
     } else {
-        jacobi_tb_kernel<K, SCALE, false><<<nxw * nch, 32, T::SMEM_LDGSTS, h->active>>>(a, maps);
+        lc.dynamicSmemBytes = T::SMEM_LDGSTS;
+        cudaLaunchKernelEx(&lc, jacobi_tb_kernel<K, SCALE, false>, a, maps);
     }
     ++h->jacobi_kernel_launches;
     return check_launch(h, "jacobi_tb_kernel");
@@ -379,11 +398,12 @@ int run_jacobi(fluid_t* h, int iters, bool scale_first, int* launches_out) {
     // one latency-bound message per launch).  If the ghost zone is too thin for that (iterations
     // raised after creation) fall back to one K-row message per launch.
     const bool deep = h->slab() && (iters + 1 <= h->G) && (iters + 1 <= h->row1 - h->row0);
-    // Overlap (deep + blocked + peer-memory or NCCL alike): the exchange and the two boundary strips
-    // of launch 1 — the only rows of it that read ghost rows — go to a second stream, the interior
-    // rows [row0+K1, row1-K1) of launch 1 run meanwhile on the compute stream.  FLUID_HALO_OVERLAP=0
-    // restores the serial order (exchange, then the whole launch).
-    static const bool overlap_off = getenv("FLUID_HALO_OVERLAP") && !strcmp(getenv("FLUID_HALO_OVERLAP"), "0");
+    // Optional overlap (deep + blocked, either transport): the exchange and the two boundary strips of
+    // launch 1 — the only rows of it that read ghost rows — go to a second stream, the interior rows
+    // [row0+K1, row1-K1) of launch 1 run meanwhile on the compute stream.
+    // Default OFF: measured on 2 B200 (4096 x 4096 per rank, 50 iterations) the split costs more than it hides —
+    // 0.310 ms per solve with it, 0.300 ms without (profiles/r02_scaling.md); FLUID_HALO_OVERLAP=1 enables it.
+    static const bool overlap_off = !(getenv("FLUID_HALO_OVERLAP") && !strcmp(getenv("FLUID_HALO_OVERLAP"), "1"));
     const int K1 = base + (extra ? 1 : 0);
     const bool overlap = deep && blocked && !overlap_off && h->stream2 && (h->row1 - h->row0) >= 2 * K1 + 4 * K1;
     if (h->slab()) {
@@ -395,10 +415,18 @@ int run_jacobi(fluid_t* h, int iters, bool scale_first, int* launches_out) {
         if (deep) {
             HaloItem it[2] = {{h->pressure.read, (size_t)W * sizeof(float), h->roff, h->row0, h->row1, iters + 1, HB_PRESSURE},
                               {h->divergence, (size_t)W * sizeof(float), h->roff, h->row0, h->row1, iters, HB_DIVERGENCE}};
+            // the neighbours' divergence rows get their tiny values flagged like the local producers do:
+            // inside the wait kernel on the peer-memory path, by a scan kernel after the NCCL group
+            h->scan.div = h->divergence; h->scan.map = h->tiny_map; h->scan.W = W; h->scan.row_off = h->roff;
+            h->scan.lo0 = std::max(h->row0 - iters, 0); h->scan.hi0 = h->row0;
+            h->scan.lo1 = h->row1; h->scan.hi1 = std::min(h->row1 + iters, H);
+            h->scan_pending = h->p2p;
             int rc = exchange_many(h, it, 2);
-            // the neighbours' divergence rows: flag their tiny values like the local producers do
-            if (!rc) rc = scan_tiny(h, std::max(h->row0 - iters, 0), h->row0);
-            if (!rc) rc = scan_tiny(h, h->row1, std::min(h->row1 + iters, H));
+            if (!rc && !h->p2p) {
+                rc = scan_tiny(h, h->scan.lo0, h->scan.hi0);
+                if (!rc) rc = scan_tiny(h, h->scan.lo1, h->scan.hi1);
+            }
+            h->scan_pending = false;
             if (rc) { h->active = h->stream; return rc; }
         } else {
             const int kmax = base + (extra ? 1 : 0);
@@ -447,7 +475,9 @@ int run_jacobi(fluid_t* h, int iters, bool scale_first, int* launches_out) {
             if (rc) return rc;
             CU(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
         } else if (blocked) {
+            h->pdl_chain = (k > 0) && !(overlap && k == 1);   // directly behind another blocked launch on this stream
             rc = launch_tb_dyn(h, K, a, sc);
+            h->pdl_chain = false;
         } else if (tb_eligible(h)) {
             dim3 b(32, 8);
             dim3 g((W / 4 + b.x - 1) / b.x, (a.out_hi - a.out_lo + b.y - 1) / b.y);
@@ -609,7 +639,10 @@ int create_common(const fluid_config* cfg, int rank, int world, const void* uid,
     if (world > 1) {
         // ghost rows: enough for the advection back-trace (3 ghost-compute rows + dt*|v|max + 2)
         // and for the deep Jacobi halo (iterations + 1), see DESIGN.md §7
-        int g = std::max(32, cfg->pressure_iterations + 2);
+        // 64 rows: a back-trace of up to (64 - 5) rows per step, i.e. |v| up to 3540 texels/s at the reference's
+        // dt <= 1/60 (vorticity clamps |v| to 1000, a pointer flick of half the canvas splats 3000); the rows
+        // cost ~4 MB of halo traffic per step per neighbour at 4096 columns, microseconds on NVLink
+        int g = std::max(64, cfg->pressure_iterations + 2);
         if (const char* e = getenv("FLUID_HALO_ROWS")) g = std::max(14, atoi(e));
         // every rank must arrive at the SAME halo height (message sizes must match), so clip with
         // the height of the shortest slab, which all ranks can compute: floor(H / world)
@@ -809,6 +842,7 @@ int fluid_set_param(fluid_t* h, int key, float v) {
         case FLUID_SPLAT_RADIUS: h->cfg.splat_radius = v; h->splat_radius_d = (double)v; break;
         case FLUID_ASPECT: h->cfg.aspect = v; h->aspect_d = (double)v; break;
         case FLUID_JACOBI_BLOCK: h->cfg.jacobi_block = (int)(v + 0.5f); break;
+        case FLUID_BACKGROUND: h->background = (int)(v + 0.5f); break;
         default: return fail(h, FLUID_ERR_INVALID, "unknown param key %d", key);
     }
     return FLUID_OK;
@@ -837,6 +871,7 @@ int fluid_get_param(fluid_t* h, int key, float* v) {
         case FLUID_SPLAT_RADIUS: *v = h->cfg.splat_radius; break;
         case FLUID_ASPECT: *v = h->cfg.aspect; break;
         case FLUID_JACOBI_BLOCK: *v = (float)h->cfg.jacobi_block; break;
+        case FLUID_BACKGROUND: *v = (float)h->background; break;
         default: return fail(h, FLUID_ERR_INVALID, "unknown param key %d", key);
     }
     return FLUID_OK;
@@ -1150,7 +1185,9 @@ int fluid_step(fluid_t* h, float dt) {
         const uint64_t l0 = h->launches, j0 = h->jacobi_kernel_launches;
         cudaGraph_t g = nullptr;
         CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        h->capturing = true;
         int rc = step_enqueue(h, false);
+        h->capturing = false;
         cudaError_t e = cudaStreamEndCapture(h->stream, &g);
         if (rc) { if (g) cudaGraphDestroy(g); return rc; }
         if (e != cudaSuccess) return fail(h, FLUID_ERR_CUDA, "stream capture of step() failed: %s", cudaGetErrorString(e));
@@ -1410,7 +1447,8 @@ int fluid_render(fluid_t* h, int width, int height, int shading, float back_r, f
     dim3 b(32, 8);
     display_kernel<<<grid2d(width, height, b), b, 0, h->stream>>>(dye_src, h->cfg.dye_w, h->cfg.dye_h,
                                                                 h->frame, width, height, shading, back_r, back_g, back_b,
-                                                                make_float2((float)(1.0 / (double)width), (float)(1.0 / (double)height)));
+                                                                make_float2((float)(1.0 / (double)width), (float)(1.0 / (double)height)),
+                                                                h->background, h->cfg.aspect);
     int rc = check_launch(h, "display_kernel"); if (rc) return rc;
     CU(cudaMemcpyAsync(host_rgba, h->frame, cells * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -1491,7 +1529,7 @@ int fluid_render_postfx(fluid_t* h, int width, int height, const fluid_postfx* f
         // ---- drawColor + drawDisplay ---------------------------------------------------------------------
         display_full_kernel<<<grid2d(width, height, b), b, 0, h->stream>>>(
             (const float4*)h->dye.read, Wd, Hd, bloom, bw, bh, sun, sw, sh, dith, dw, dh, h->frame, width, height,
-            back_r, back_g, back_b);
+            back_r, back_g, back_b, h->background, h->cfg.aspect);
         int r = check_launch(h, "post-FX kernels", nk + 5); if (r) return r;
         CU(cudaMemcpyAsync(host_rgba, h->frame, cells * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
         if (host_bloom) CU(cudaMemcpyAsync(host_bloom, bloom, (size_t)bw * bh * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
@@ -1503,6 +1541,13 @@ int fluid_render_postfx(fluid_t* h, int width, int height, const fluid_postfx* f
     cleanup();
     return rc;
 }
+
+void* fluid_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (bytes == 0 || cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void fluid_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int fluid_sync(fluid_t* h) {
     if (!h) return FLUID_ERR_INVALID;

@@ -14,6 +14,7 @@
 enum { HB_VELOCITY = 0, HB_PRESSURE = 1, HB_DYE = 2, HB_DIVERGENCE = 3 };
 struct HaloItem { void* base; size_t row_bytes; int off, r0, r1, n; int which; };
 
+struct ScanArgs { const float* div; unsigned char* map; int W, row_off, lo0, hi0, lo1, hi1; };
 struct PushSeg { const float4* src; float4* dst; unsigned long long n4; };
 struct PushArgs {
     PushSeg seg[8];
@@ -25,6 +26,7 @@ struct PushArgs {
     unsigned* counter;         // block-completion counter (local)
     int* err;                  // set when a bounded spin times out (reported as FLUID_ERR_HALO)
     unsigned long long* dbg;   // FLUID_DEBUG_HALO_TIMING: [0] sum wait-free ns [1] sum push ns [2] sum wait-ready ns [3] count [4] t_start
+    ScanArgs scan;             // divergence ghost strips to scan for tiny values once they have arrived (W == 0: none)
 };
 
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
@@ -45,7 +47,7 @@ __device__ __forceinline__ void spin_until(const unsigned* flag, unsigned seq, i
     }
 }
 
-// The whole producer side of one halo exchange in ONE kernel:
+// One halo exchange in ONE kernel, producer and consumer side:
 //   (a) tell the neighbours my ghost rows may be overwritten (this kernel is stream-ordered after
 //       every kernel of mine that read them), (b) wait until theirs are free, (c) store my boundary
 //       rows straight into their ghost rows — dst pointers are the neighbours' arenas mapped through
@@ -84,16 +86,25 @@ __global__ void __launch_bounds__(256) halo_push_kernel(PushArgs a) {
             if (a.dbg) { atomicAdd(a.dbg + 1, global_ns() - a.dbg[4]); atomicAdd(a.dbg + 3, 1ull); }
         }
     }
-}
-
-// (e) consumer side: one thread acquires the neighbours' "ready" words; kernels after it in the
-// stream then read the ghost rows the neighbours stored.
-__global__ void halo_wait_kernel(const unsigned* my_flags, int present_below, int present_above,
-                                 unsigned seq, int* err, unsigned long long* dbg) {
-    const unsigned long long t0 = dbg ? global_ns() : 0;
-    if (present_below) spin_until(my_flags + 0, seq, err);
-    if (present_above) spin_until(my_flags + 1, seq, err);
-    if (dbg) atomicAdd(dbg + 2, global_ns() - t0);
+    // (e) consumer side in the SAME kernel (every block is resident: the grid is at most 2 blocks per SM):
+    // acquire the neighbours' "ready" words, then (f) flag tiny values in the divergence strips that arrived.
+    if (threadIdx.x == 0) {
+        const unsigned long long t0 = (a.dbg && blockIdx.x == 0) ? global_ns() : 0;
+        if (a.present[0]) spin_until(a.my_flags + 0, a.seq, a.err);
+        if (a.present[1]) spin_until(a.my_flags + 1, a.seq, a.err);
+        if (a.dbg && blockIdx.x == 0) atomicAdd(a.dbg + 2, global_ns() - t0);
+    }
+    __syncthreads();
+    if (a.scan.W > 0) {
+        const ScanArgs& sc = a.scan;
+        const int n0 = max(sc.hi0 - sc.lo0, 0) * sc.W, n1 = max(sc.hi1 - sc.lo1, 0) * sc.W;
+        const int mw = fk::tiny_map_w(sc.W);
+        for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n0 + n1; k += gridDim.x * blockDim.x) {
+            const int q = k < n0 ? k : k - n0;
+            const int j = (k < n0 ? sc.lo0 : sc.lo1) + q / sc.W, i = q % sc.W;
+            if (fk::is_tiny_div(sc.div[(size_t)(j - sc.row_off) * sc.W + i])) sc.map[(j / fk::TINY_CH) * mw + i / fk::TINY_CW] = 1;
+        }
+    }
 }
 
 int exchange_p2p(fluid_t* h, const HaloItem* it, int count) {
@@ -132,11 +143,13 @@ int exchange_p2p(fluid_t* h, const HaloItem* it, int count) {
         }
     }
     const unsigned blocks = (unsigned)std::min<unsigned long long>(std::max<unsigned long long>((total4 + 255) / 256, 1), (unsigned long long)h->sm_count * 2);
-    halo_push_kernel<<<blocks, 256, 0, h->active>>>(pa);
+    if (h->scan_pending) {          // this exchange carries divergence ghost rows: their tiny-value scan rides along
+        pa.scan = ScanArgs{h->scan.div, h->scan.map, h->scan.W, h->scan.row_off, h->scan.lo0, h->scan.hi0, h->scan.lo1, h->scan.hi1};
+        h->scan_pending = false;
+    }
+    halo_push_kernel<<<blocks, 256, 0, h->active>>>(pa);     // push + handshake + wait + scan: one launch per exchange
     int rc = check_launch(h, "halo_push_kernel"); if (rc) return rc;
-    halo_wait_kernel<<<1, 1, 0, h->active>>>(pa.my_flags, pa.present[0], pa.present[1], pa.seq, pa.err, pa.dbg);
-    rc = check_launch(h, "halo_wait_kernel"); if (rc) return rc;
-    h->halo_kernel_launches += 2;
+    h->halo_kernel_launches += 1;
     ++h->halo_groups;
     return FLUID_OK;
 }

@@ -522,6 +522,12 @@ template <int K, bool SCALE, bool TMA>
 __global__ void FLUID_TB_BOUNDS jacobi_tb_kernel(JacobiArgs a, const __grid_constant__ TmapPair maps) {
     using T = TB<K>;
     extern __shared__ __align__(128) float4 smem4[];
+    // Programmatic dependent launch: back-to-back blocked launches of one solve are chained with
+    // cudaLaunchAttributeProgrammaticStreamSerialization, so the NEXT launch's CTAs are already
+    // resident (index math done, parked at griddepcontrol.wait) while this grid drains — the
+    // single-wave tail and the launch gap overlap instead of adding up.  Both instructions are
+    // no-ops for a launch without the attribute.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int lane = threadIdx.x;
     const int nxw = (a.W + T::VALID - 1) / T::VALID;
     const int wid = blockIdx.x;
@@ -546,6 +552,8 @@ __global__ void FLUID_TB_BOUNDS jacobi_tb_kernel(JacobiArgs a, const __grid_cons
     const int y1 = min(y0 + a.rows_per_chunk, seg_hi);
     const int ys = max(y0 - K, 0);                    // first input row
     const int ye = min(y1 - 1 + K, H - 1);            // last input row
+
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // everything below reads what the previous launch wrote
 
     // ---- does the divergence this stream reads hold a value that defeats the fma contraction? ----
     bool exact = false;

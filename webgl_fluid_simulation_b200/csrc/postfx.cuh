@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(256) display_full_kernel(const float4* __restr
                                                            const float* __restrict__ sun, int sw, int sh,
                                                            const float* __restrict__ dither, int dw, int dh,
                                                            float4* __restrict__ out, int w, int h, float br_, float bg_,
-                                                           float bb_) {
+                                                           float bb_, int bg_mode, float aspect) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
     if (i >= w || j >= h) return;
     const float tsx = (float)(1.0 / (double)w), tsy = (float)(1.0 / (double)h);
@@ -159,8 +159,7 @@ __global__ void __launch_bounds__(256) display_full_kernel(const float4* __restr
         cc[k] = ck + bk;
     }
     const float a = fmaxf(cc[0], fmaxf(cc[1], cc[2]));
-    const float k1 = 1.0f - a;
-    out[(size_t)j * w + i] = make_float4(cc[0] + br_ * k1, cc[1] + bg_ * k1, cc[2] + bb_ * k1, a + 1.0f * k1);
+    out[(size_t)j * w + i] = blend_over_background(cc[0], cc[1], cc[2], a, bg_mode, br_, bg_, bb_, aspect, uvx, uvy);
 }
 
 }  // namespace fk

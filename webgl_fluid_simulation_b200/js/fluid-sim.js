@@ -1,5 +1,13 @@
 // fluid-sim.js — the reference's simulation surface in its own language, over the N-API shim.
 //
+// The host-side helpers below (pointerPrototype, HSVtoRGB, wrap, generateColor, multipleSplats,
+// splatPointer, calcDeltaTime, updateColors, applyInputs, updatePointer*Data, correctDelta*) keep
+// the names, argument order and arithmetic of PavelDoGreat/WebGL-Fluid-Simulation's script.js so
+// that this module is a drop-in for its simulation path; those parts are
+//     Copyright (c) 2017 Pavel Dobryakov, MIT License (see LICENSE at the repository root).
+// No shader / compute code of the reference is reproduced: all simulation work happens in
+// libfluid_b200 (hand-written CUDA).
+//
 // NOT EXECUTED IN THIS REPOSITORY: the build image has no Node (`node --version`: not found) and
 // no browser, so this file is the integration artefact for a maintainer, kept in lock-step with
 // its tested Python twin webgl_fluid_simulation_b200/sim.py (same structure, same names).
@@ -20,6 +28,8 @@ const PARAM = {
     DENSITY_DISSIPATION: 0, VELOCITY_DISSIPATION: 1, PRESSURE: 2, PRESSURE_ITERATIONS: 3,
     CURL: 4, SPLAT_RADIUS: 5, ASPECT: 6, JACOBI_BLOCK: 7,
 };
+const FLAG = { UNFUSED: 0x1, NO_GRAPH: 0x2, NAIVE_JACOBI: 0x4, TILED_PASSES: 0x8, HALF_STORAGE: 0x10 };
+const STAT = { launches: 0, jacobiLaunches: 1, haloLaunches: 2, haloExchanges: 3, graphCaptures: 4, graphLaunches: 5, haloTransportP2P: 6 };
 
 function pointerPrototype () {                                  // S:87-98
     this.id = -1;
@@ -31,7 +41,7 @@ function pointerPrototype () {                                  // S:87-98
     this.deltaY = 0;
     this.down = false;
     this.moved = false;
-    this.color = [30, 0, 300];
+    this.color = { r: 30, g: 0, b: 300 };                       // an {r,g,b} object like generateColor() returns (splat reads .r/.g/.b)
 }
 
 function HSVtoRGB (h, s, v) {                                   // S:1573-1597
@@ -70,9 +80,11 @@ class FluidSimulation {
             CURL: 30,
             SPLAT_RADIUS: 0.25,
             SPLAT_FORCE: 6000,
+            SHADING: true,
             COLORFUL: true,
             COLOR_UPDATE_SPEED: 10,
             PAUSED: false,
+            BACK_COLOR: { r: 0, g: 0, b: 0 },
         }, config);
         this.canvas = canvas;
         this.random = options.random || Math.random;            // injectable for reproducible runs
@@ -201,9 +213,55 @@ class FluidSimulation {
         return dt;
     }
 
+    // ---- pointer helpers (the caller side of splat(); the DOM listeners S:1464-1525 stay with the page) ----
+    updatePointerDownData (pointer, id, posX, posY) {           // S:1527-1538
+        pointer.id = id;
+        pointer.down = true;
+        pointer.moved = false;
+        pointer.texcoordX = posX / this.canvas.width;
+        pointer.texcoordY = 1.0 - posY / this.canvas.height;
+        pointer.prevTexcoordX = pointer.texcoordX;
+        pointer.prevTexcoordY = pointer.texcoordY;
+        pointer.deltaX = 0;
+        pointer.deltaY = 0;
+        pointer.color = this.generateColor();
+    }
+
+    updatePointerMoveData (pointer, posX, posY) {               // S:1540-1548
+        pointer.prevTexcoordX = pointer.texcoordX;
+        pointer.prevTexcoordY = pointer.texcoordY;
+        pointer.texcoordX = posX / this.canvas.width;
+        pointer.texcoordY = 1.0 - posY / this.canvas.height;
+        pointer.deltaX = this.correctDeltaX(pointer.texcoordX - pointer.prevTexcoordX);
+        pointer.deltaY = this.correctDeltaY(pointer.texcoordY - pointer.prevTexcoordY);
+        pointer.moved = Math.abs(pointer.deltaX) > 0 || Math.abs(pointer.deltaY) > 0;
+    }
+
+    updatePointerUpData (pointer) { pointer.down = false; }     // S:1550-1552
+
+    correctDeltaX (delta) {                                     // S:1554-1558
+        const aspectRatio = this._aspect();
+        if (aspectRatio < 1) delta *= aspectRatio;
+        return delta;
+    }
+
+    correctDeltaY (delta) {                                     // S:1560-1564
+        const aspectRatio = this._aspect();
+        if (aspectRatio > 1) delta /= aspectRatio;
+        return delta;
+    }
+
+    // render(target) of S:1296-1317 with BLOOM = SUNRAYS = false: Float32Array RGBA, row 0 = bottom
+    render (width = this.canvas.width, height = this.canvas.height) {
+        const bc = this.config.BACK_COLOR;                      // normalizeColor, S:1599-1606
+        return native.render(this._h, width, height, !!this.config.SHADING, bc.r / 255, bc.g / 255, bc.b / 255);
+    }
+
+    stat (name) { return native.stat(this._h, STAT[name]); }
+    destroy () { if (this._h != null) { native.destroy(this._h); this._h = null; } }   // frees device memory now, not at GC
     readField (name) { return native.read(this._h, FIELD[name]); }
     writeField (name, f32) { native.write(this._h, FIELD[name], f32); }
     sync () { native.sync(this._h); }
 }
 
-module.exports = { FluidSimulation, pointerPrototype, HSVtoRGB, wrap, FIELD, PARAM };
+module.exports = { FluidSimulation, pointerPrototype, HSVtoRGB, wrap, FIELD, PARAM, FLAG, STAT };

@@ -53,6 +53,14 @@ napi_status napi_create_typedarray(napi_env env, napi_typedarray_type type, size
 napi_status napi_get_typedarray_info(napi_env env, napi_value typedarray, napi_typedarray_type* type,
                                      size_t* length, void** data, napi_value* arraybuffer, size_t* byte_offset);
 napi_status napi_throw_error(napi_env env, const char* code, const char* msg);
+napi_status napi_create_object(napi_env env, napi_value* result);
+napi_status napi_set_named_property(napi_env env, napi_value object, const char* utf8name, napi_value value);
+napi_status napi_create_external_arraybuffer(napi_env env, void* external_data, size_t byte_length,
+                                             napi_finalize finalize_cb, void* finalize_hint, napi_value* result);
+napi_status napi_get_arraybuffer_info(napi_env env, napi_value arraybuffer, void** data, size_t* byte_length);
+napi_status napi_get_value_uint32(napi_env env, napi_value value, uint32_t* result);
+napi_status napi_get_value_bool(napi_env env, napi_value value, bool* result);
+napi_status napi_is_exception_pending(napi_env env, bool* result);
 napi_status napi_create_string_utf8(napi_env env, const char* str, size_t length, napi_value* result);
 #ifdef __cplusplus
 }

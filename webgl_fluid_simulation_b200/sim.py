@@ -11,6 +11,11 @@ reference's own language for when Node is available; this Python twin is what th
 
 There is no CPU or PyTorch fallback: constructing a simulation without the built library or
 without a B200 raises.
+
+The host-side helpers (Pointer, HSVtoRGB, wrap, generateColor, multipleSplats, splatPointer,
+calcDeltaTime, updateColors, applyInputs, updatePointer*Data, correctDelta*) follow script.js line
+for line because mirroring that interface is the point; those parts are Copyright (c) 2017 Pavel
+Dobryakov, MIT License (see LICENSE).
 """
 from __future__ import annotations
 
@@ -340,16 +345,20 @@ class FluidSimulation:
         a = np.ascontiguousarray(array, np.float32)
         self._check(self._L.fluid_write(self._h, FIELD[name], a.ctypes.data_as(C.c_void_p), a.size))
 
-    def render(self, width=None, height=None) -> np.ndarray:
-        """render(target), S:1296-1317, for BLOOM = SUNRAYS = TRANSPARENT = false: background colour
-        + shaded dye, (height, width, 4) float32 RGBA, row 0 = bottom.  Defaults to the canvas size
-        (target == null branch, S:1332-1333)."""
+    def render(self, width=None, height=None, target=False) -> np.ndarray:
+        """render(target), S:1296-1317: (height, width, 4) float32 RGBA, row 0 = bottom.  Defaults
+        to the canvas size (target == null branch, S:1332-1333).  config.TRANSPARENT: the display is
+        drawn over the checkerboard on the screen (target=False, S:1311-1312) and bare, un-blended,
+        into a capture target (target=True: what captureScreenshot renders into, S:287-299)."""
         w = int(width or self.canvas["width"]); h = int(height or self.canvas["height"])
         bc = self.config["BACK_COLOR"]                       # normalizeColor, S:1599-1606
         out = np.empty((h, w, 4), np.float32)
         cfg = self.config
-        if cfg.get("TRANSPARENT"):
-            raise NotImplementedError("TRANSPARENT (checkerboard) display is not built")
+        bg = 0 if not cfg.get("TRANSPARENT") else (2 if target else 1)
+        if self._pushed.get("BACKGROUND") != bg:
+            self._check(self._L.fluid_set_param(self._h, PARAM["BACKGROUND"], float(bg)))
+            self._pushed["BACKGROUND"] = bg
+        self._push_config()                                  # the checkerboard uses canvas.width / canvas.height (S:1327)
         if cfg.get("BLOOM") or cfg.get("SUNRAYS"):
             # built for the reference's default keyword set only: SHADING + BLOOM + SUNRAYS
             if not (cfg.get("BLOOM") and cfg.get("SUNRAYS") and cfg.get("SHADING")):

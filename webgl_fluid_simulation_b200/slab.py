@@ -19,7 +19,7 @@ from dataclasses import dataclass
 
 KMAX = 12
 DEFAULT_BLOCK = 10
-DEFAULT_HALO = 32
+DEFAULT_HALO = 64
 VELOCITY_GHOST = 3
 
 
