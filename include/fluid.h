@@ -204,6 +204,11 @@ int fluid_pressure_solve_host(fluid_t* h, const float* div_host, float* pressure
  * floats (row 0 = bottom, not yet quantised to 8 bits) to host memory.  back_* are BACK_COLOR / 255. */
 int fluid_render(fluid_t* h, int width, int height, int shading, float back_r, float back_g,
                  float back_b, float* host_rgba, size_t n_floats);
+/* On a slab handle fluid_render draws (and returns) only the band of target rows [*y0, *y1) that
+ * corresponds to the dye rows the rank owns — width * (*y1 - *y0) RGBA texels — after refreshing
+ * the few dye ghost rows the display / shading taps reach; on a single GPU the band is the whole
+ * target.  Ranks concatenate their bands in rank order. */
+int fluid_render_band(fluid_t* h, int height, int* y0, int* y1);
 
 /* The same with the reference's desktop defaults SHADING = BLOOM = SUNRAYS = true (S:70-84):
  * applyBloom (S:1350-1394), applySunrays + blur (S:1396-1419), then the display shader with all three

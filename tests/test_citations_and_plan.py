@@ -13,7 +13,9 @@ REF = "/root/reference/script.js"
 FILES = ["include/fluid.h", "DESIGN.md", "INTEGRATION.md", "oracle/fluid_oracle.c", "oracle/fluid_oracle.h",
          "oracle/glsl_exec.py", "webgl_fluid_simulation_b200/sim.py", "webgl_fluid_simulation_b200/js/fluid-sim.js",
          "webgl_fluid_simulation_b200/csrc/jacobi.cuh", "webgl_fluid_simulation_b200/csrc/passes.cuh",
-         "webgl_fluid_simulation_b200/csrc/fluid.cu"]
+         "webgl_fluid_simulation_b200/csrc/fluid.cu", "webgl_fluid_simulation_b200/csrc/stream_passes.cuh",
+         "webgl_fluid_simulation_b200/csrc/half_passes.cuh", "webgl_fluid_simulation_b200/csrc/postfx.cuh",
+         "webgl_fluid_simulation_b200/napi/fluid_napi.c", "README.md"]
 
 
 @pytest.mark.skipif(not os.path.exists(REF), reason="reference not mounted")

@@ -9,6 +9,10 @@ KEYS = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__b
         "launch__registers_per_thread", "launch__waves_per_multiprocessor",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum",
+        "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "l1tex__throughput.avg.pct_of_peak_sustained_active", "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__t_sector_hit_rate.pct",
+        "sm__cycles_active.avg", "sm__cycles_elapsed.max",
         "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "lts__t_bytes.sum", "l1tex__t_bytes.sum",
         "smsp__warps_eligible.avg.per_cycle_active", "smsp__warps_active.avg.per_cycle_active",
@@ -30,7 +34,12 @@ def main():
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     out = [f"# ncu summary of `{rep}` (`ncu --set full --clock-control none`)", ""]
+    seen = set()
     for r in rows[2:]:
+        name = r[hdr.index("Kernel Name")] if "Kernel Name" in hdr else ""
+        if name in seen:            # one table per distinct kernel (the first capture of it)
+            continue
+        seen.add(name)
         out.append("| metric | value | unit |"); out.append("|---|---|---|")
         for k in KEYS:
             if k in hdr:

@@ -17,17 +17,30 @@ from webgl_fluid_simulation_b200.distributed import create_slab_simulation  # no
 W = int(os.environ.get("SLAB_W", 512)); H = int(os.environ.get("SLAB_H", 768))
 WD = int(os.environ.get("SLAB_WD", 1024)); HD = int(os.environ.get("SLAB_HD", 1536))
 ITERS = int(os.environ.get("SLAB_ITERS", 23)); STEPS = int(os.environ.get("SLAB_STEPS", 4))
+RESIZE = os.environ.get("SLAB_RESIZE")             # "W,H,WD,HD": initFramebuffers() to these sizes after the steps, then 2 more steps
+FAST = float(os.environ.get("SLAB_FAST", 0))     # texels/s of an extra splat placed ON a slab edge (back-trace reach test)
 
 
 def drive(sim, seed=5):
     rs = np.random.RandomState(seed)
     sim.random = lambda: float(rs.random_sample())
     sim.multipleSplats(6)
+    if FAST:   # the fastest thing a pointer flick produces, right on the boundary between two slabs, aimed across it
+        sim.splat(0.5, 0.5, 0.3 * FAST, FAST, (0.9, 0.2, 0.1)); sim.splat(0.25, 0.5, 0.0, -FAST, (0.1, 0.8, 0.3))
     for k in range(STEPS):
         sim.step(0.016666)
         if k == 1:
             sim.multipleSplats(2)
-    return {n: sim.readField(n) for n in ("velocity", "dye", "pressure", "divergence")}
+    out = {n: sim.readField(n) for n in ("velocity", "dye", "pressure", "divergence")}
+    out["frame_"] = sim.render(256, 192)                 # a slab rank returns its band of the 256 x 192 target
+    if RESIZE:                                           # resizeDoubleFBO on a live simulation (S:1116-1126), slab or not
+        sim._sizes = tuple(int(x) for x in RESIZE.split(","))
+        sim.initFramebuffers()
+        out["resized_velocity"] = sim.readField("velocity"); out["resized_dye"] = sim.readField("dye")
+        for _ in range(2):
+            sim.step(0.016666)
+        out["after_velocity"] = sim.readField("velocity"); out["after_dye"] = sim.readField("dye")
+    return out
 
 
 def main():
@@ -39,12 +52,14 @@ def main():
     sim = create_slab_simulation(cfg, W, H, device=local, sizes=(W, H, WD, HD))
     mine = drive(sim)
     # also the bench metric's entry point on slabs
+    Ws, Hs = (tuple(int(x) for x in RESIZE.split(","))[:2]) if RESIZE else (W, H)      # the grid the handles hold by now
     rng = np.random.default_rng(1)
-    pfull = rng.standard_normal((H, W)).astype(np.float32); dfull = rng.uniform(-1, 1, (H, W)).astype(np.float32)
+    pfull = rng.standard_normal((Hs, Ws)).astype(np.float32); dfull = rng.uniform(-1, 1, (Hs, Ws)).astype(np.float32)
     r0 = sim._dims("pressure")[3]; rows = sim._dims("pressure")[1]
     sim.writeField("pressure", pfull[r0:r0 + rows]); sim.writeField("divergence", dfull[r0:r0 + rows])
     sim.pass_("pressure_solve"); mine["solve"] = sim.readField("pressure")
     sim.close()
+    mine["frame"] = mine.pop("frame_")
     gathered = [None] * world
     dist.all_gather_object(gathered, {k: (v, ) for k, v in mine.items()})
     ok, msgs = True, []
@@ -54,6 +69,7 @@ def main():
         one.writeField("pressure", pfull); one.writeField("divergence", dfull)
         one.pass_("pressure_solve"); ref["solve"] = one.readField("pressure")
         one.close()
+        ref["frame"] = ref.pop("frame_")
         for name, full in ref.items():
             got = np.concatenate([g[name][0] for g in gathered], axis=0)
             same = got.shape == full.shape and np.array_equal(got.view(np.uint32), full.view(np.uint32))

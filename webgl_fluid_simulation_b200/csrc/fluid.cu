@@ -53,6 +53,8 @@ struct fluid {
     uint64_t launches = 0;
     uint64_t jacobi_kernel_launches = 0;   // Jacobi kernels only (fluid_stat FLUID_STAT_JACOBI_LAUNCHES)
     uint64_t halo_kernel_launches = 0;     // halo_push / halo_wait kernels of the peer-memory transport
+    uint64_t div_epoch = 1, div_sent_epoch = 0;   // slab: the divergence ghost rows are re-sent only after divergence was rewritten
+    int div_sent_rows = 0;
     bool pdl_chain = false;                // the next blocked Jacobi launch directly follows another one of the same solve
     bool capturing = false;                // inside the stream capture of a step graph
     bool half = false;                     // FLUID_FLAG_HALF_STORAGE: fields are fp16 (half_passes.cuh), single GPU only
@@ -204,6 +206,7 @@ int alloc_tiny_map(fluid_t* h) {
 // before a pass that recomputes divergence everywhere (the pass then flags cells itself)
 int clear_tiny_map(fluid_t* h) {
     CU(cudaMemsetAsync(h->tiny_map, 0, h->tiny_map_bytes, h->stream));
+    ++h->div_epoch;                       // every writer of divergence comes through here
     return FLUID_OK;
 }
 // divergence rows [j_lo, j_hi) came from outside (host write, neighbour rank): flag their cells
@@ -415,14 +418,20 @@ int run_jacobi(fluid_t* h, int iters, bool scale_first, int* launches_out) {
         if (deep) {
             HaloItem it[2] = {{h->pressure.read, (size_t)W * sizeof(float), h->roff, h->row0, h->row1, iters + 1, HB_PRESSURE},
                               {h->divergence, (size_t)W * sizeof(float), h->roff, h->row0, h->row1, iters, HB_DIVERGENCE}};
+            // divergence is constant during a solve and often across solves (a host that iterates the solve on
+            // one right-hand side, bench.py's loop): its ghost rows — and their tiny-value flags — are still in
+            // place unless some pass rewrote divergence since they were last received (SPMD-identical decision)
+            const bool send_div = h->div_sent_epoch != h->div_epoch || h->div_sent_rows < iters;
+            const int nitems = send_div ? 2 : 1;
             // the neighbours' divergence rows get their tiny values flagged like the local producers do:
             // inside the wait kernel on the peer-memory path, by a scan kernel after the NCCL group
             h->scan.div = h->divergence; h->scan.map = h->tiny_map; h->scan.W = W; h->scan.row_off = h->roff;
             h->scan.lo0 = std::max(h->row0 - iters, 0); h->scan.hi0 = h->row0;
             h->scan.lo1 = h->row1; h->scan.hi1 = std::min(h->row1 + iters, H);
-            h->scan_pending = h->p2p;
-            int rc = exchange_many(h, it, 2);
-            if (!rc && !h->p2p) {
+            h->scan_pending = h->p2p && send_div;
+            int rc = exchange_many(h, it, nitems);
+            if (send_div) { h->div_sent_epoch = h->div_epoch; h->div_sent_rows = iters; }
+            if (!rc && !h->p2p && send_div) {
                 rc = scan_tiny(h, h->scan.lo0, h->scan.hi0);
                 if (!rc) rc = scan_tiny(h, h->scan.lo1, h->scan.hi1);
             }
@@ -536,6 +545,7 @@ int alloc_fields(fluid_t* h) {
     }
     { int rc = alloc_tiny_map(h); if (rc) return rc; }
     build_tmaps(h);
+    h->div_sent_epoch = 0;                               // fresh buffers: no divergence ghost rows in place yet
     if (h->half) {
         hs::fill_alpha_kernel<<<(unsigned)((nd + 255) / 256), 256, 0, h->stream>>>((hs::h4*)h->dye.read, nd);
         hs::fill_alpha_kernel<<<(unsigned)((nd + 255) / 256), 256, 0, h->stream>>>((hs::h4*)h->dye.write, nd);
@@ -597,6 +607,33 @@ int not_on_slab(fluid_t* h, const char* what) {
                 "fluid_step / fluid_splat / fluid_pass_pressure_solve / fluid_pass_jacobi / read / write", what);
 }
 
+// Row ownership + ghost-zone heights of rank `rank` of `world` for a sim_h / dye_h grid.
+// Returns false when the slabs are too short for the minimum 14-row halo.
+bool slab_geometry(fluid_t* h, int H, int Hd, int iters) {
+    const int rank = h->rank, world = h->world;
+    h->row0 = (int)((long long)H * rank / world);  h->row1 = (int)((long long)H * (rank + 1) / world);
+    h->drow0 = (int)((long long)Hd * rank / world); h->drow1 = (int)((long long)Hd * (rank + 1) / world);
+    h->G = h->Gd = 0;
+    if (world > 1) {
+        // ghost rows: enough for the advection back-trace (3 ghost-compute rows + dt*|v|max + 2)
+        // and for the deep Jacobi halo (iterations + 1).
+        // 64 rows: a back-trace of up to (64 - 5) rows per step, i.e. |v| up to 3540 texels/s at the reference's
+        // dt <= 1/60 (vorticity clamps |v| to 1000, a pointer flick of half the canvas splats 3000); the rows
+        // cost ~4 MB of halo traffic per step per neighbour at 4096 columns, microseconds on NVLink
+        int g = std::max(64, iters + 2);
+        if (const char* e = getenv("FLUID_HALO_ROWS")) g = std::max(14, atoi(e));
+        // every rank must arrive at the SAME halo height (message sizes must match), so clip with
+        // the height of the shortest slab, which all ranks can compute: floor(H / world)
+        const int per = std::max(1, (Hd + H - 1) / H);
+        g = std::min(g, std::min(H / world, (Hd / world) / per));
+        h->G = g;
+        h->Gd = g * per;                              // same physical reach on the dye grid
+        if (g < 14) return false;
+    }
+    h->roff = h->row0 - h->G; h->droff = h->drow0 - h->Gd;
+    return true;
+}
+
 // shared by fluid_create and fluid_create_slab
 int create_common(const fluid_config* cfg, int rank, int world, const void* uid, fluid_t** out) {
     fluid_t* h = nullptr;
@@ -633,29 +670,10 @@ int create_common(const fluid_config* cfg, int rank, int world, const void* uid,
         int rc = fail(nullptr, FLUID_ERR_INVALID, "FLUID_FLAG_HALF_STORAGE is a single-GPU mode");
         delete h; return rc;
     }
-    const int H = cfg->sim_h, Hd = cfg->dye_h;
-    h->row0 = (int)((long long)H * rank / world);  h->row1 = (int)((long long)H * (rank + 1) / world);
-    h->drow0 = (int)((long long)Hd * rank / world); h->drow1 = (int)((long long)Hd * (rank + 1) / world);
-    if (world > 1) {
-        // ghost rows: enough for the advection back-trace (3 ghost-compute rows + dt*|v|max + 2)
-        // and for the deep Jacobi halo (iterations + 1), see DESIGN.md §7
-        // 64 rows: a back-trace of up to (64 - 5) rows per step, i.e. |v| up to 3540 texels/s at the reference's
-        // dt <= 1/60 (vorticity clamps |v| to 1000, a pointer flick of half the canvas splats 3000); the rows
-        // cost ~4 MB of halo traffic per step per neighbour at 4096 columns, microseconds on NVLink
-        int g = std::max(64, cfg->pressure_iterations + 2);
-        if (const char* e = getenv("FLUID_HALO_ROWS")) g = std::max(14, atoi(e));
-        // every rank must arrive at the SAME halo height (message sizes must match), so clip with
-        // the height of the shortest slab, which all ranks can compute: floor(H / world)
-        const int per = std::max(1, (Hd + H - 1) / H);
-        g = std::min(g, std::min(H / world, (Hd / world) / per));
-        h->G = g;
-        h->Gd = g * per;                              // same physical reach on the dye grid
-        if (g < 14) {
-            int rc = fail(nullptr, FLUID_ERR_INVALID, "slabs of %d rows are too short for a 14-row halo: use fewer GPUs", H / world);
-            delete h; return rc;
-        }
+    if (!slab_geometry(h, cfg->sim_h, cfg->dye_h, cfg->pressure_iterations)) {
+        int rc = fail(nullptr, FLUID_ERR_INVALID, "slabs of %d rows are too short for a 14-row halo: use fewer GPUs", cfg->sim_h / world);
+        delete h; return rc;
     }
-    h->roff = h->row0 - h->G; h->droff = h->drow0 - h->Gd;
     if (const char* e = getenv("FLUID_JACOBI_ROWS")) h->jacobi_rows_override = atoi(e);
     if (const char* e = getenv("FLUID_JACOBI_WARPS")) h->jacobi_warps_per_sm = atoi(e);
     auto body = [&]() -> int {
@@ -1004,7 +1022,8 @@ static int do_advect_velocity(fluid_t* h, Grid out) {
     if (h->half) {
         hs::advect_kernel<hs::h2, float2><<<hs_grid(out.W, out.H), HS_BLOCK, 0, h->stream>>>(
             (const hs::h2*)h->velocity.read, out.W, out.H, (const hs::h2*)h->velocity.read, (hs::h2*)h->velocity.write, out.W, out.H,
-            h->dt_dev, h->cfg.velocity_dissipation);
+            h->dt_dev, h->cfg.velocity_dissipation, (float)(1.0 / (double)out.W), (float)(1.0 / (double)out.H),
+            (float)(1.0 / (double)out.W), (float)(1.0 / (double)out.H));
         int rc = check_launch(h, "hs::advect_kernel"); if (rc) return rc;
         swap_v(h);
         return FLUID_OK;
@@ -1033,7 +1052,8 @@ static int do_advect_dye(fluid_t* h) {
     if (h->half) {
         hs::advect_kernel<hs::h4, float4><<<hs_grid(h->cfg.dye_w, h->cfg.dye_h), HS_BLOCK, 0, h->stream>>>(
             (const hs::h2*)h->velocity.read, h->cfg.sim_w, h->cfg.sim_h, (const hs::h4*)h->dye.read, (hs::h4*)h->dye.write,
-            h->cfg.dye_w, h->cfg.dye_h, h->dt_dev, h->cfg.density_dissipation);
+            h->cfg.dye_w, h->cfg.dye_h, h->dt_dev, h->cfg.density_dissipation, (float)(1.0 / (double)h->cfg.sim_w),
+            (float)(1.0 / (double)h->cfg.sim_h), (float)(1.0 / (double)h->cfg.dye_w), (float)(1.0 / (double)h->cfg.dye_h));
         int rc = check_launch(h, "hs::advect_kernel"); if (rc) return rc;
         swap_dye(h);
         return FLUID_OK;
@@ -1260,7 +1280,44 @@ int fluid_splat(fluid_t* h, float x, float y, float dx, float dy, float r, float
 int fluid_resize(fluid_t* h, int sim_w, int sim_h, int dye_w, int dye_h) {
     if (!h) return FLUID_ERR_INVALID;
     if (sim_w < 1 || sim_h < 1 || dye_w < 1 || dye_h < 1) return fail(h, FLUID_ERR_INVALID, "bad size");
-    if (h->slab()) return not_on_slab(h, "fluid_resize");
+    if (h->slab()) {
+        // Collective among the ranks of the group (all call it with the same sizes).  The new rows a rank
+        // owns sample old rows it owns +- ceil(old/new) + 2: refresh that many ghost rows of the old
+        // velocity and dye, resample into a NEW arena, drop the old one.  Peer mappings die with the old
+        // arena: the group is back on NCCL until the launcher exports / connects again
+        // (distributed.connect_peers).
+        const int ow = h->cfg.sim_w, oh = h->cfg.sim_h, odw = h->cfg.dye_w, odh = h->cfg.dye_h;
+        const int need_v = (oh + sim_h - 1) / sim_h + 2, need_d = (odh + dye_h - 1) / dye_h + 2;
+        if (need_v > h->G || need_d > h->Gd)
+            return fail(h, FLUID_ERR_HALO, "resize by this factor needs %d / %d ghost rows, the slab keeps %d / %d", need_v, need_d, h->G, h->Gd);
+        int rc;
+        if ((rc = exchange_rows(h, HB_VELOCITY, h->velocity.read, (size_t)ow * sizeof(float2), h->roff, h->row0, h->row1, need_v))) return rc;
+        if ((rc = exchange_rows(h, HB_DYE, h->dye.read, (size_t)odw * sizeof(float4), h->droff, h->drow0, h->drow1, need_d))) return rc;
+        CU(cudaStreamSynchronize(h->stream));
+        // keep the old arena alive while the new one is filled
+        char* old_arena = h->arena; const float2* old_v = (const float2*)h->velocity.read; const float4* old_d = (const float4*)h->dye.read;
+        const int old_roff = h->roff, old_droff = h->droff;
+        for (auto& p : h->peer) if (p.present && p.base) { cudaIpcCloseMemHandle(p.base); p.base = nullptr; p.present = false; }
+        h->p2p = false;
+        h->arena = nullptr;
+        h->cfg.sim_w = sim_w; h->cfg.sim_h = sim_h; h->cfg.dye_w = dye_w; h->cfg.dye_h = dye_h;
+        if (!slab_geometry(h, sim_h, dye_h, h->cfg.pressure_iterations)) {
+            cudaFree(old_arena);
+            return fail(h, FLUID_ERR_INVALID, "new slabs of %d rows are too short for a 14-row halo", sim_h / h->world);
+        }
+        cudaFree(h->tiny_map); h->tiny_map = nullptr;
+        if ((rc = alloc_fields(h))) { cudaFree(old_arena); return rc; }
+        dim3 b(64, 4);
+        resample_slab_kernel<<<grid2d(sim_w, h->row1 - h->row0, b), b, 0, h->stream>>>(old_v, ow, oh, old_roff, (float2*)h->velocity.read, sim_w, sim_h,
+                                                                                         h->roff, h->row0, h->row1);
+        resample_slab_kernel<<<grid2d(dye_w, h->drow1 - h->drow0, b), b, 0, h->stream>>>(old_d, odw, odh, old_droff, (float4*)h->dye.read, dye_w, dye_h,
+                                                                                           h->droff, h->drow0, h->drow1);
+        rc = check_launch(h, "resample_slab_kernel", 2);
+        CU(cudaStreamSynchronize(h->stream));
+        cudaFree(old_arena);
+        h->v_ghost_valid = false;                            // the +-3 velocity ghost rows are rebuilt by the next step
+        return rc;
+    }
     CU(cudaStreamSynchronize(h->stream));
     drop_graphs(h);                                          // graphs hold the old buffers' addresses
     if (h->half) {
@@ -1422,19 +1479,40 @@ int fluid_pressure_solve_host(fluid_t* h, const float* div_host, float* p_host, 
     return FLUID_OK;
 }
 
-// render(target) of S:1296-1317 for config.BLOOM = config.SUNRAYS = false, TRANSPARENT = false:
-// background colour, then the display shader (optionally SHADING) blended over it.
+// The band of a width x height target this handle draws: the whole target on one GPU, rows
+// [height*rank/world, height*(rank+1)/world) on a slab rank (the same fractions as the dye rows it owns).
+int fluid_render_band(fluid_t* h, int height, int* y0, int* y1) {
+    if (!h || height < 1 || !y0 || !y1) return FLUID_ERR_INVALID;
+    *y0 = (int)((long long)height * h->rank / h->world);
+    *y1 = (int)((long long)height * (h->rank + 1) / h->world);
+    return FLUID_OK;
+}
+
+// render(target) of S:1296-1317 for config.BLOOM = config.SUNRAYS = false: the background selected by
+// FLUID_BACKGROUND (colour / checkerboard / none), then the display shader (optionally SHADING) blended over it.
 int fluid_render(fluid_t* h, int width, int height, int shading, float back_r, float back_g,
                  float back_b, float* host_rgba, size_t n_floats) {
     if (!h || !host_rgba || width < 1 || height < 1) return fail(h, FLUID_ERR_INVALID, "bad argument");
-    if (h->slab()) return not_on_slab(h, "fluid_render");
-    const size_t cells = (size_t)width * height;
-    if (n_floats != 4 * cells) return fail(h, FLUID_ERR_INVALID, "render target has %zu floats, caller passed %zu", 4 * cells, n_floats);
+    int y0, y1;
+    fluid_render_band(h, height, &y0, &y1);
+    const size_t cells = (size_t)width * (y1 - y0);
+    if (n_floats != 4 * cells) return fail(h, FLUID_ERR_INVALID, "render target band has %zu floats, caller passed %zu", 4 * cells, n_floats);
+    if (cells == 0) return FLUID_OK;
     if (cells > h->frame_cells) {
         CU(cudaStreamSynchronize(h->stream));
         cudaFree(h->frame); h->frame = nullptr; h->frame_cells = 0;
         CU(cudaMalloc((void**)&h->frame, cells * sizeof(float4)));
         h->frame_cells = cells;
+    }
+    if (h->slab()) {
+        // the band's display + shading taps reach ceil(Hd / height) + 2 dye rows beyond the owned ones:
+        // refresh that many ghost rows (the ghost rows of dye.read are stale after advection)
+        const int need = std::min(h->Gd, (h->cfg.dye_h + height - 1) / height + 2);
+        int rc = exchange_rows(h, HB_DYE, h->dye.read, (size_t)h->cfg.dye_w * sizeof(float4), h->droff, h->drow0, h->drow1, need);
+        if (rc) return rc;
+        if ((h->cfg.dye_h + height - 1) / height + 2 > h->Gd)
+            return fail(h, FLUID_ERR_HALO, "render target of %d rows needs %d dye ghost rows, the slab keeps %d", height,
+                        (h->cfg.dye_h + height - 1) / height + 2, h->Gd);
     }
     const float4* dye_src = (const float4*)h->dye.read;
     if (h->half) {                                   // the sampler widens fp16 texels exactly; shading is fp32 as in the shader
@@ -1445,15 +1523,16 @@ int fluid_render(fluid_t* h, int width, int height, int shading, float back_r, f
         dye_src = (const float4*)h->scratch;
     }
     dim3 b(32, 8);
-    display_kernel<<<grid2d(width, height, b), b, 0, h->stream>>>(dye_src, h->cfg.dye_w, h->cfg.dye_h,
-                                                                h->frame, width, height, shading, back_r, back_g, back_b,
-                                                                make_float2((float)(1.0 / (double)width), (float)(1.0 / (double)height)),
-                                                                h->background, h->cfg.aspect);
+    display_kernel<<<grid2d(width, y1 - y0, b), b, 0, h->stream>>>(dye_src, h->cfg.dye_w, h->cfg.dye_h,
+                                                                   h->frame, width, height, shading, back_r, back_g, back_b,
+                                                                   make_float2((float)(1.0 / (double)width), (float)(1.0 / (double)height)),
+                                                                   h->background, h->cfg.aspect, h->droff, y0, y1);
     int rc = check_launch(h, "display_kernel"); if (rc) return rc;
     CU(cudaMemcpyAsync(host_rgba, h->frame, cells * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return FLUID_OK;
 }
+
 
 // render(null) of S:1296-1317 with config.SHADING = BLOOM = SUNRAYS = true (the reference's desktop
 // defaults S:70-84), TRANSPARENT = false: applyBloom (S:1350-1394), applySunrays + blur(…, 1)
@@ -1529,7 +1608,8 @@ int fluid_render_postfx(fluid_t* h, int width, int height, const fluid_postfx* f
         // ---- drawColor + drawDisplay ---------------------------------------------------------------------
         display_full_kernel<<<grid2d(width, height, b), b, 0, h->stream>>>(
             (const float4*)h->dye.read, Wd, Hd, bloom, bw, bh, sun, sw, sh, dith, dw, dh, h->frame, width, height,
-            back_r, back_g, back_b, h->background, h->cfg.aspect);
+            back_r, back_g, back_b, h->background, h->cfg.aspect,
+            make_float4((float)(1.0 / (double)width), (float)(1.0 / (double)height), (float)((double)width / (double)dw), (float)((double)height / (double)dh)));
         int r = check_launch(h, "post-FX kernels", nk + 5); if (r) return r;
         CU(cudaMemcpyAsync(host_rgba, h->frame, cells * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
         if (host_bloom) CU(cudaMemcpyAsync(host_bloom, bloom, (size_t)bw * bh * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));

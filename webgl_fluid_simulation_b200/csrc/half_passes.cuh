@@ -145,12 +145,10 @@ __device__ __forceinline__ float4 bilerp_h<h4, float4>(const h4* __restrict__ te
 template <typename T, typename F>
 __global__ void __launch_bounds__(256) advect_kernel(const h2* __restrict__ vel, int Wv, int Hv, const T* __restrict__ src,
                                                      T* __restrict__ out, int W, int H, const float* __restrict__ dtp,
-                                                     float dissipation) {
+                                                     float dissipation, float tsx, float tsy, float dsx, float dsy) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
     if (i >= W || j >= H) return;
-    const float dt = __ldg(dtp);
-    const float tsx = (float)(1.0 / (double)Wv), tsy = (float)(1.0 / (double)Hv);
-    const float dsx = (float)(1.0 / (double)W), dsy = (float)(1.0 / (double)H);
+    const float dt = __ldg(dtp);       // tsx.. = fp32 of the JS doubles 1/W (S:1061-1062), computed on the host
     const float uvx = ((float)i + 0.5f) / (float)W, uvy = ((float)j + 0.5f) / (float)H;
     const float2 vv = bilerp_h<h2, float2>(vel, Wv, bilerp_taps(uvx, uvy, tsx, tsy, Wv, Hv));
     const float cx = uvx - (dt * vv.x) * tsx, cy = uvy - (dt * vv.y) * tsy;

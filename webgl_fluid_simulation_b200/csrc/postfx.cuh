@@ -130,11 +130,11 @@ __global__ void __launch_bounds__(256) display_full_kernel(const float4* __restr
                                                            const float* __restrict__ sun, int sw, int sh,
                                                            const float* __restrict__ dither, int dw, int dh,
                                                            float4* __restrict__ out, int w, int h, float br_, float bg_,
-                                                           float bb_, int bg_mode, float aspect) {
+                                                           float bb_, int bg_mode, float aspect, float4 ts) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
     if (i >= w || j >= h) return;
-    const float tsx = (float)(1.0 / (double)w), tsy = (float)(1.0 / (double)h);
-    const float dsx = (float)((double)w / (double)dw), dsy = (float)((double)h / (double)dh);
+    const float tsx = ts.x, tsy = ts.y;     // 1/width, 1/height (S:1337) and getTextureScale (S:1626-1631): JS doubles, narrowed on the host
+    const float dsx = ts.z, dsy = ts.w;
     const float uvx = ((float)i + 0.5f) / (float)w, uvy = ((float)j + 0.5f) / (float)h;
     const float4 c = linear_fetch4(dye, Wd, Hd, uvx, uvy);
     const float4 lc = linear_fetch4(dye, Wd, Hd, uvx - tsx, uvy), rc = linear_fetch4(dye, Wd, Hd, uvx + tsx, uvy);

@@ -213,6 +213,10 @@ class FluidSimulation:
         else:                                            # resizeDoubleFBO branch, S:1116-1126
             self._check(self._L.fluid_resize(self._h, simRes["width"], simRes["height"],
                                              dyeRes["width"], dyeRes["height"]))
+            if self._world > 1 and getattr(self, "halo_transport", "nccl") == "p2p":
+                # the peer mappings died with the old arena: export / connect again (collective)
+                from .distributed import connect_peers
+                self.halo_transport = "p2p" if connect_peers(self) else "nccl"
         self._pushed = {}
         self._push_config()
 
@@ -378,6 +382,10 @@ class FluidSimulation:
                 bc["r"] / 255, bc["g"] / 255, bc["b"] / 255, out.ctypes.data_as(C.c_void_p), out.size,
                 self.last_bloom.ctypes.data_as(C.c_void_p), self.last_sunrays.ctypes.data_as(C.c_void_p)))
             return out
+        y0, y1 = C.c_int(), C.c_int()                        # a slab rank draws its band of the target only
+        self._check(self._L.fluid_render_band(self._h, h, C.byref(y0), C.byref(y1)))
+        out = out[: y1.value - y0.value]
+        self.render_band = (y0.value, y1.value)
         self._check(self._L.fluid_render(self._h, w, h, 1 if self.config["SHADING"] else 0,
                                          bc["r"] / 255, bc["g"] / 255, bc["b"] / 255,
                                          out.ctypes.data_as(C.c_void_p), out.size))
