@@ -7,9 +7,10 @@ A "step" is one pass of the metric's hot path over one batch of synthetic input:
 solve of step() — clear (p <- PRESSURE*p, S:1253-1257) + PRESSURE_ITERATIONS Jacobi sweeps
 (S:1259-1266) — on BASELINE.json configs[2]: 4096x4096 fp32, 50 iterations, fields resident in HBM.
 `value`    = W*H*iters*steps / device time (CUDA events on the library's own stream).
-`parity`   = checked BEFORE timing, on the timed inputs: temporally blocked == one-sweep-per-launch
-             bit for bit, and at N>1 the CRC32 of every rank's owned rows == the same rows of a
-             single-GPU solve of the whole grid (the oracle comparison itself lives in tests/).
+`parity`   = checked BEFORE timing, on the timed inputs, after three successive solves: temporally
+             blocked == one-sweep-per-launch bit for bit, and at N>1 the CRC32 of every rank's owned
+             rows == the same rows of a single-GPU run of the whole grid (the oracle comparison itself
+             lives in tests/).
 `e2e`      = the same solve through the C-ABI call with HOST buffers (fluid_pressure_solve_host:
              H2D divergence + pressure from pinned memory, solve, D2H pressure, all inside the call).
 `e2e_step` = the drop-in frame: splat(...) -> step(dt) -> read dye into pinned host memory.
@@ -323,9 +324,15 @@ def main():
     parity = None
     if not args.quick:
         parity = {}
-        load(sim); sim.pass_("pressure_solve"); mine = sim.readField("pressure")
+        # THREE successive solves (each one: clear pass + the Jacobi loop on the previous result), so that the
+        # steady state of the timed loop is what is compared — on slabs, solves 2 and 3 start from ghost rows
+        # that are already in place (divergence not re-sent; pressure rows stored by the neighbour's last launch)
+        def solve3(s_):
+            for _ in range(3):
+                s_.pass_("pressure_solve")
+        load(sim); solve3(sim); mine = sim.readField("pressure")
         nsim = make_sim(flags=pkg.FLAG_NAIVE_JACOBI, jb=1)
-        load(nsim); nsim.pass_("pressure_solve"); naive = nsim.readField("pressure"); nsim.close()
+        load(nsim); solve3(nsim); naive = nsim.readField("pressure"); nsim.close()
         same = bool(np.array_equal(mine.view(np.uint32), naive.view(np.uint32)))
         del naive
         if dist:
@@ -342,14 +349,15 @@ def main():
                 one = pkg.FluidSimulation(cfg, 1024, 1024, device=local, jacobi_block=args.jacobi_block,
                                           sizes=(W, rows * world, 64, 64 * world))
                 one.writeField("pressure", gp); one.writeField("divergence", gd)
-                one.pass_("pressure_solve"); full = one.readField("pressure"); one.close()
+                solve3(one); full = one.readField("pressure"); one.close()
                 ok = all(crc(full[r * rows:(r + 1) * rows]) == crcs[r] for r in range(world))
                 del gp, gd, full
             box = [ok]
             dist.broadcast_object_list(box, src=0)
             parity["slabs_eq_single_gpu_bitwise"] = bool(box[0])
-            parity["slabs_check"] = (f"CRC32 of every rank's owned rows ({W}x{rows}) vs the same rows of a single-GPU "
-                                     f"solve of the {W}x{rows * world} grid on rank 0's GPU")
+            parity["slabs_check"] = (f"CRC32 of every rank's owned rows ({W}x{rows}) after 3 successive solves vs the same rows "
+                                     f"of a single-GPU run of the {W}x{rows * world} grid on rank 0's GPU")
+        parity["solves"] = 3
         del mine
         load(sim)
 

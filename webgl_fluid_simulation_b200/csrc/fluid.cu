@@ -96,6 +96,11 @@ struct fluid {
     } peer[2];                       // [0] = rank-1 (below), [1] = rank+1 (above)
     bool p2p = false;
     uint32_t p2p_seq = 0;
+    // pressure ghost rows stored by the neighbours' last Jacobi launch (jacobi.cuh, TbSync): sequence number of
+    // the last mirrored solve, whether pressure.read's ghost rows still hold it, and how many rows deep
+    uint32_t mir_seq = 0;
+    bool p_mirror_valid = false;
+    int p_mirror_rows = 0;
     // divergence ghost rows of the exchange about to be issued: the peer-memory wait kernel scans them (halo.cuh)
     struct { const float* div; unsigned char* map; int W, row_off, lo0, hi0, lo1, hi1; } scan{};
     bool scan_pending = false;
@@ -350,6 +355,8 @@ bool tb_eligible(const fluid_t* h) {
 // message of its own); divergence ghosts are exchanged once per solve (it is constant in the loop).
 int run_jacobi(fluid_t* h, int iters, bool scale_first, int* launches_out) {
     int nl = 0;
+    const bool p_ghosts_mirrored = h->p_mirror_valid;    // every path below rewrites pressure
+    h->p_mirror_valid = false;
     const int W = h->cfg.sim_w, H = h->cfg.sim_h;
     JacobiArgs a{};
     a.div = h->divergence; a.W = W; a.H = H; a.row_off = h->roff; a.out_lo = h->row0; a.out_hi = h->row1;
@@ -409,6 +416,15 @@ int run_jacobi(fluid_t* h, int iters, bool scale_first, int* launches_out) {
     static const bool overlap_off = !(getenv("FLUID_HALO_OVERLAP") && !strcmp(getenv("FLUID_HALO_OVERLAP"), "1"));
     const int K1 = base + (extra ? 1 : 0);
     const bool overlap = deep && blocked && !overlap_off && h->stream2 && (h->row1 - h->row0) >= 2 * K1 + 4 * K1;
+    // Peer-memory transport, two or more blocked launches: the last launch of this solve stores the pressure
+    // rows the neighbours need next time into their ghost rows itself (TbSync in jacobi.cuh), and if the
+    // previous solve did so — nothing wrote pressure since — this solve starts without a pressure message.
+    // FLUID_HALO_MIRROR=1 enables it (default: the explicit exchange).
+    static const bool mirror_off = !(getenv("FLUID_HALO_MIRROR") && !strcmp(getenv("FLUID_HALO_MIRROR"), "1"));
+    const bool mirror = deep && blocked && h->p2p && nlaunch >= 2 && !mirror_off && !overlap && !tb_use_tma(h);
+    const bool p_in_place = mirror && p_ghosts_mirrored && h->p_mirror_rows >= iters + 1;
+    unsigned* const my_flags = h->slab() ? (unsigned*)(h->arena + h->off_flags) : nullptr;
+    auto peer_flags = [&](int side) { return (unsigned*)(h->peer[side].base + h->peer[side].off_flags); };
     if (h->slab()) {
         if (overlap) {
             CU(cudaEventRecord(h->ev_fork, h->stream));
@@ -416,20 +432,23 @@ int run_jacobi(fluid_t* h, int iters, bool scale_first, int* launches_out) {
             h->active = h->stream2;
         }
         if (deep) {
-            HaloItem it[2] = {{h->pressure.read, (size_t)W * sizeof(float), h->roff, h->row0, h->row1, iters + 1, HB_PRESSURE},
-                              {h->divergence, (size_t)W * sizeof(float), h->roff, h->row0, h->row1, iters, HB_DIVERGENCE}};
+            const HaloItem itp = {h->pressure.read, (size_t)W * sizeof(float), h->roff, h->row0, h->row1, iters + 1, HB_PRESSURE};
+            const HaloItem itd = {h->divergence, (size_t)W * sizeof(float), h->roff, h->row0, h->row1, iters, HB_DIVERGENCE};
             // divergence is constant during a solve and often across solves (a host that iterates the solve on
             // one right-hand side, bench.py's loop): its ghost rows — and their tiny-value flags — are still in
             // place unless some pass rewrote divergence since they were last received (SPMD-identical decision)
             const bool send_div = h->div_sent_epoch != h->div_epoch || h->div_sent_rows < iters;
-            const int nitems = send_div ? 2 : 1;
+            HaloItem it[2];
+            int nitems = 0;
+            if (!p_in_place) it[nitems++] = itp;
+            if (send_div) it[nitems++] = itd;
             // the neighbours' divergence rows get their tiny values flagged like the local producers do:
             // inside the wait kernel on the peer-memory path, by a scan kernel after the NCCL group
             h->scan.div = h->divergence; h->scan.map = h->tiny_map; h->scan.W = W; h->scan.row_off = h->roff;
             h->scan.lo0 = std::max(h->row0 - iters, 0); h->scan.hi0 = h->row0;
             h->scan.lo1 = h->row1; h->scan.hi1 = std::min(h->row1 + iters, H);
             h->scan_pending = h->p2p && send_div;
-            int rc = exchange_many(h, it, nitems);
+            int rc = nitems ? exchange_many(h, it, nitems) : FLUID_OK;
             if (send_div) { h->div_sent_epoch = h->div_epoch; h->div_sent_rows = iters; }
             if (!rc && !h->p2p && send_div) {
                 rc = scan_tiny(h, h->scan.lo0, h->scan.hi0);
@@ -462,6 +481,34 @@ int run_jacobi(fluid_t* h, int iters, bool scale_first, int* launches_out) {
                 if (rc) return rc;
             }
             a.out_lo = std::max(h->row0 - ext, 0); a.out_hi = std::min(h->row1 + ext, H);
+        }
+        a.sy = TbSync{};
+        if (mirror) {
+            const unsigned seq = h->mir_seq + 1;
+            if (k == 0 && p_in_place) {                          // wait for the previous solve's mirrored rows
+                for (int s = 0; s < 2; ++s)
+                    if (h->peer[s].present) a.sy.pre_wait[s] = my_flags + 66 + s;
+                a.sy.pre_seq = h->mir_seq; a.sy.own_lo = h->row0; a.sy.own_hi = h->row1;
+            }
+            if (k == nlaunch - 2) {                              // last reader of the ghost rows the neighbours will overwrite
+                a.sy.ticket = my_flags + 72;
+                for (int s = 0; s < 2; ++s)
+                    if (h->peer[s].present) a.sy.done_flag[s] = peer_flags(s) + (s == 0 ? 65 : 64);
+                a.sy.done_seq = seq;
+            }
+            if (last) {
+                const int pidx = ((char*)h->pressure.write == h->arena + h->off_p[0]) ? 0 : 1;
+                for (int s = 0; s < 2; ++s) {
+                    const fluid::Peer& P = h->peer[s];
+                    if (!P.present) continue;
+                    a.sy.mirror[s] = (float*)(P.base + P.off_p[pidx]) - (ptrdiff_t)P.roff * W;
+                    a.sy.mir_lo[s] = s == 0 ? h->row0 : h->row1 - (iters + 1);
+                    a.sy.mir_hi[s] = s == 0 ? h->row0 + (iters + 1) : h->row1;
+                    a.sy.mir_wait[s] = my_flags + 64 + s;
+                    a.sy.done_flag[s] = peer_flags(s) + (s == 0 ? 67 : 66);
+                }
+                a.sy.mir_seq = seq; a.sy.ticket = my_flags + 73; a.sy.done_seq = seq;
+            }
         }
         const bool sc = scale_first && k == 0;
         int rc;
@@ -503,6 +550,7 @@ int run_jacobi(fluid_t* h, int iters, bool scale_first, int* launches_out) {
         if (rc) return rc;
         swap_p(h); ++nl;
     }
+    if (mirror) { ++h->mir_seq; h->p_mirror_valid = true; h->p_mirror_rows = iters + 1; }
     if (launches_out) *launches_out = nl;
     return FLUID_OK;
 }
@@ -819,7 +867,7 @@ int fluid_p2p_disable(fluid_t* h) {
     if (!h) return FLUID_ERR_INVALID;
     if (h->stream) CU(cudaStreamSynchronize(h->stream));
     for (auto& p : h->peer) if (p.present && p.base) { cudaIpcCloseMemHandle(p.base); p.base = nullptr; p.present = false; }
-    h->p2p = false;
+    h->p2p = false; h->p_mirror_valid = false;
     return FLUID_OK;
 }
 
@@ -1298,7 +1346,7 @@ int fluid_resize(fluid_t* h, int sim_w, int sim_h, int dye_w, int dye_h) {
         char* old_arena = h->arena; const float2* old_v = (const float2*)h->velocity.read; const float4* old_d = (const float4*)h->dye.read;
         const int old_roff = h->roff, old_droff = h->droff;
         for (auto& p : h->peer) if (p.present && p.base) { cudaIpcCloseMemHandle(p.base); p.base = nullptr; p.present = false; }
-        h->p2p = false;
+        h->p2p = false; h->p_mirror_valid = false;
         h->arena = nullptr;
         h->cfg.sim_w = sim_w; h->cfg.sim_h = sim_h; h->cfg.dye_w = dye_w; h->cfg.dye_h = dye_h;
         if (!slab_geometry(h, sim_h, dye_h, h->cfg.pressure_iterations)) {
@@ -1449,6 +1497,7 @@ int fluid_write(fluid_t* h, int field, const float* host, size_t n_floats) {
     CU(cudaMemcpyAsync(p, host, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     if (field == FLUID_FIELD_VELOCITY) h->v_ghost_valid = false;   // ghosts rebuilt by the next step
+    if (field == FLUID_FIELD_PRESSURE) h->p_mirror_valid = false;  // the neighbours' ghost copies are stale now
     if (field == FLUID_FIELD_DIVERGENCE) {                          // host-provided divergence: rebuild the map
         int rc = clear_tiny_map(h); if (rc) return rc;
         if ((rc = scan_tiny(h, h->row0, h->row1))) return rc;
@@ -1471,6 +1520,7 @@ int fluid_pressure_solve_host(fluid_t* h, const float* div_host, float* p_host, 
     // make the copies asynchronous DMA.  Either way all three copies are inside this call.
     CU(cudaMemcpyAsync(h->divergence + go, div_host, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync((float*)h->pressure.read + go, p_host, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    h->p_mirror_valid = false;
     int rc = clear_tiny_map(h); if (rc) return rc;
     if ((rc = scan_tiny(h, h->row0, h->row1))) return rc;
     rc = run_jacobi(h, iters, true, nullptr); if (rc) return rc;

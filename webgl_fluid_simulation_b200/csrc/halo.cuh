@@ -29,23 +29,7 @@ struct PushArgs {
     ScanArgs scan;             // divergence ghost strips to scan for tiny values once they have arrived (W == 0: none)
 };
 
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
-    unsigned v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long global_ns() {
-    unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t;
-}
-// bounded spin: a neighbour that never arrives costs 4 s and an error flag, never a hung GPU
-__device__ __forceinline__ void spin_until(const unsigned* flag, unsigned seq, int* err) {
-    const unsigned long long t0 = global_ns();
-    while ((int)(ld_acquire_sys(flag) - seq) < 0) {
-        if (global_ns() - t0 > 4000000000ull) { *err = 2; break; }
-        __nanosleep(100);
-    }
-}
+using fk::ld_acquire_sys; using fk::st_release_sys; using fk::global_ns; using fk::spin_until;   // jacobi.cuh
 
 // One halo exchange in ONE kernel, producer and consumer side:
 //   (a) tell the neighbours my ghost rows may be overwritten (this kernel is stream-ordered after

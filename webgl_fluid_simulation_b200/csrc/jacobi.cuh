@@ -33,6 +33,46 @@
 
 namespace fk {
 
+// ---- cross-GPU hand-offs of a slab solve (peer-memory transport; everything null on one GPU) ------
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t;
+}
+// bounded spin: a neighbour that never arrives costs 4 s and an error flag, never a hung GPU
+__device__ __forceinline__ void spin_until(const unsigned* flag, unsigned seq, int* err) {
+    const unsigned long long t0 = global_ns();
+    while ((int)(ld_acquire_sys(flag) - seq) < 0) {
+        if (global_ns() - t0 > 4000000000ull) { *err = 2; break; }
+        __nanosleep(100);
+    }
+}
+
+// The LAST blocked launch of a solve stores the rows its neighbours will need as ghost rows of the
+// NEXT solve straight into their arenas (NVLink stores from the compute kernel: no separate message,
+// no exchange kernel between two solves), guarded by two flag hand-offs:
+//   * "done reading": the neighbour's PENULTIMATE launch was the last reader of the ghost rows about
+//     to be overwritten (same ping-pong buffer); its last CTA to finish release-stores the solve's
+//     sequence number into my flag word, and my mirroring warps acquire it first;
+//   * "mirror ready": my last CTA to finish release-stores the sequence number into the neighbour's
+//     flag word; the streams of its next first launch that read ghost rows acquire it first.
+struct TbSync {
+    const unsigned* pre_wait[2];   // [0] below, [1] above: streams reading rows outside [own_lo, own_hi) wait for *flag >= pre_seq
+    unsigned pre_seq;
+    int own_lo, own_hi;
+    float* mirror[2];              // neighbour's copy of pout, offset so that GLOBAL row j starts at mirror + j*W
+    int mir_lo[2], mir_hi[2];      // global rows [lo, hi) of mine the neighbour on that side keeps as ghost rows
+    const unsigned* mir_wait[2];   // "done reading" words (local), value mir_seq
+    unsigned mir_seq;
+    unsigned* ticket;              // CTA completion counter (local); null: this launch signals nothing
+    unsigned* done_flag[2];        // words in the neighbours' arenas that receive done_seq when the whole grid is done
+    unsigned done_seq;
+};
+
 struct JacobiArgs {
     const float* pin;    // local row 0 of the source pressure buffer
     const float* div;    // local row 0 of divergence
@@ -48,6 +88,7 @@ struct JacobiArgs {
     // wait for the halo while the interior runs): chunks 0..nch1-1 tile [out_lo, out_hi), the rest
     // tile [seg2_lo, seg2_hi).  nch1 <= 0: single range.
     int nch1, seg2_lo, seg2_hi;
+    TbSync sy;
 };
 
 // the two tensor maps a temporally blocked launch reads through (TMA staging); 64-byte aligned
@@ -507,6 +548,52 @@ __device__ FLUID_TB_EXACT_ATTR void tb_stream_exact(const JacobiArgs& a, const v
     else tb_stream<K, SCALE, false, true, TMA>(a, tm_p, tm_d, smem4, lane, x0, lc, gx, rev, lane_out, y0, y1, ys, ye);
 }
 
+// Slab epilogue of a stream (last launch of a solve): copy the rows this warp just produced that lie in
+// a neighbour's ghost zone into the neighbour's buffer.  The warp re-reads its own stores (same
+// thread, same address: program order), waits for the neighbour's "done reading" first.
+// Written WITHOUT lane-dependent control flow (predicated PTX instead of if (lane ...)): code that may
+// diverge after the stream makes the compiler drop its "this one-warp CTA is always converged"
+// assumption for the whole kernel, and the shuffles of the hot loops get divergence scaffolding.
+__device__ __forceinline__ void st_v4_if(float4* p, const float4 v, const bool on) {
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %5, 0; @q st.global.v4.f32 [%0], {%1, %2, %3, %4}; }"
+                 ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"((unsigned)on) : "memory");
+}
+__device__ __forceinline__ void tb_mirror(const JacobiArgs& a, const int gx, const bool lane_out, const int y0, const int y1) {
+    const int W4 = a.W >> 2;
+    const int col = lane_out ? (gx >> 2) : 0;
+    const float4* own = reinterpret_cast<const float4*>(a.pout) - (ptrdiff_t)a.row_off * W4 + col;
+#pragma unroll 1
+    for (int s = 0; s < 2; ++s) {
+        if (a.sy.mirror[s] == nullptr) continue;
+        const int lo = max(y0, a.sy.mir_lo[s]), hi = min(y1, a.sy.mir_hi[s]);
+        if (lo >= hi) continue;
+        spin_until(a.sy.mir_wait[s], a.sy.mir_seq, a.err);          // every lane polls the same word: uniform
+        float4* dst = reinterpret_cast<float4*>(a.sy.mirror[s]) + col;
+#pragma unroll 4
+        for (int r = lo; r < hi; ++r) st_v4_if(dst + (ptrdiff_t)r * W4, own[(ptrdiff_t)r * W4], lane_out);
+    }
+    __threadfence_system();
+}
+
+// Grid-completion signal: the last CTA to get here release-stores done_seq into the neighbours' words.
+__device__ __forceinline__ void tb_signal_done(const JacobiArgs& a, const int lane) {
+    __threadfence_system();
+    // every lane is past its fence before lane 0 takes the ticket (a vote, not __syncwarp: see above)
+    const unsigned first = (__all_sync(0xffffffffu, 1) && lane == 0) ? 1u : 0u;
+    unsigned t;
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %1, 0; mov.u32 %0, 0xffffffff; @q atom.global.add.u32 %0, [%2], 1; }"
+                 : "=r"(t) : "r"(first), "l"(a.sy.ticket) : "memory");
+    const unsigned last = (t == gridDim.x - 1) ? 1u : 0u;              // lane 0 of the last CTA only
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q st.global.u32 [%1], 0; @q fence.acq_rel.sys; }"
+                 ::"r"(last), "l"(a.sy.ticket) : "memory");
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        if (a.sy.done_flag[s] == nullptr) continue;
+        asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q st.release.sys.global.u32 [%1], %2; }"
+                     ::"r"(last), "l"(a.sy.done_flag[s]), "r"(a.sy.done_seq) : "memory");
+    }
+}
+
 // One warp per CTA: every quantity that steers control flow derives from blockIdx and kernel
 // arguments only, so the compiler can prove the warp converged at each shuffle (no WARPSYNC /
 // BSSY scaffolding) and keeps loop state in uniform registers.
@@ -555,6 +642,12 @@ __global__ void FLUID_TB_BOUNDS jacobi_tb_kernel(JacobiArgs a, const __grid_cons
 
     asm volatile("griddepcontrol.wait;" ::: "memory");      // everything below reads what the previous launch wrote
 
+    // slab, first launch of a solve whose pressure ghost rows were stored by the neighbours' previous
+    // last launch: the streams that read those rows acquire "mirror ready" first
+    // (every lane polls the same word — warp-uniform control flow, see tb_mirror)
+    if (a.sy.pre_wait[0] != nullptr && ys < a.sy.own_lo) spin_until(a.sy.pre_wait[0], a.sy.pre_seq, a.err);
+    if (a.sy.pre_wait[1] != nullptr && ye >= a.sy.own_hi) spin_until(a.sy.pre_wait[1], a.sy.pre_seq, a.err);
+
     // ---- does the divergence this stream reads hold a value that defeats the fma contraction? ----
     bool exact = false;
 #ifndef FLUID_TB_NO_EXACT          // tuning builds only: measures what the second instantiation costs in code size
@@ -579,6 +672,8 @@ __global__ void FLUID_TB_BOUNDS jacobi_tb_kernel(JacobiArgs a, const __grid_cons
     } else {
         tb_stream_exact<K, SCALE, TMA>(a, tp, td, smem4, lane, x0, lc, gx, rev, lane_out, y0, y1, ys, ye, any_rev);
     }
+    if (a.sy.mirror[0] != nullptr || a.sy.mirror[1] != nullptr) tb_mirror(a, gx, lane_out, y0, y1);
+    if (a.sy.ticket != nullptr) tb_signal_done(a, lane);
 }
 
 // ---- producers of the tiny-divergence map ----------------------------------------------------------
