@@ -144,7 +144,11 @@ void fluid_destroy(fluid_t* h);
 
 /* initFramebuffers() on a live simulation (S:982-1010 else-branches + resizeDoubleFBO S:1116-1126):
  * velocity and dye are bilinearly resampled to the new size (copyShader through a LINEAR sampler),
- * pressure / divergence / curl are re-created zeroed. */
+ * pressure / divergence / curl are re-created zeroed.
+ * On a slab handle the call is collective (same sizes on every rank): ghost rows of the old velocity and
+ * dye are refreshed, the rank's new rows are resampled into a new arena, and the peer-memory mappings
+ * are dropped (export / connect again, or stay on NCCL).  FLUID_ERR_HALO: the factor needs more ghost
+ * rows than the slab keeps. */
 int fluid_resize(fluid_t* h, int sim_w, int sim_h, int dye_w, int dye_h);
 
 /* ---- the hot path ---------------------------------------------------------------------------- */

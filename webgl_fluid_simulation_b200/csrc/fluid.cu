@@ -101,6 +101,8 @@ struct fluid {
     uint32_t mir_seq = 0;
     bool p_mirror_valid = false;
     int p_mirror_rows = 0;
+    fk::TbSync tb_sync{};                      // hand-offs of the NEXT blocked launch (launch_tb: SYNC instantiation when tb_sync_on)
+    bool tb_sync_on = false;
     // divergence ghost rows of the exchange about to be issued: the peer-memory wait kernel scans them (halo.cuh)
     struct { const float* div; unsigned char* map; int W, row_off, lo0, hi0, lo1, hi1; } scan{};
     bool scan_pending = false;
@@ -290,16 +292,23 @@ int launch_tb(fluid_t* h, const JacobiArgs& a) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cudaLaunchConfig_t lc{};
     lc.gridDim = dim3(nxw * nch); lc.blockDim = dim3(32); lc.stream = h->active;
-    lc.attrs = attr; lc.numAttrs = (h->pdl_chain && !pdl_off && !h->capturing) ? 1 : 0;
+    // FLUID_PDL_GRAPH=1: also while a step graph is captured (the launch becomes a programmatic edge)
+    static const bool pdl_graph = getenv("FLUID_PDL_GRAPH") && !strcmp(getenv("FLUID_PDL_GRAPH"), "1");
+    lc.attrs = attr; lc.numAttrs = (h->pdl_chain && !pdl_off && (!h->capturing || pdl_graph)) ? 1 : 0;
     if (tb_use_tma(h)) {
         const int k = (a.pin == h->tmaps.p_ptr[0]) ? 0 : 1;
         memcpy(maps.p, &h->tmaps.p[k], sizeof(CUtensorMap));
         memcpy(maps.d, &h->tmaps.d, sizeof(CUtensorMap));
         lc.dynamicSmemBytes = T::SMEM_TMA;
-        cudaLaunchKernelEx(&lc, jacobi_tb_kernel<K, SCALE, true>, a, maps);                       // one warp per CTA
+        { TbArgs<false> ta; static_cast<JacobiArgs&>(ta) = a; cudaLaunchKernelEx(&lc, jacobi_tb_kernel<K, SCALE, true, false>, ta, maps); }   // one warp per CTA
+    } else if (h->tb_sync_on) {                       // slab launch with hand-offs (run_jacobi fills h->tb_sync)
+        lc.dynamicSmemBytes = T::SMEM_LDGSTS;
+        TbArgs<true> ta; static_cast<JacobiArgs&>(ta) = a; ta.sy = h->tb_sync;
+        cudaLaunchKernelEx(&lc, jacobi_tb_kernel<K, SCALE, false, true>, ta, maps);
     } else {
         lc.dynamicSmemBytes = T::SMEM_LDGSTS;
-        cudaLaunchKernelEx(&lc, jacobi_tb_kernel<K, SCALE, false>, a, maps);
+        TbArgs<false> ta; static_cast<JacobiArgs&>(ta) = a;
+        cudaLaunchKernelEx(&lc, jacobi_tb_kernel<K, SCALE, false, false>, ta, maps);
     }
     ++h->jacobi_kernel_launches;
     return check_launch(h, "jacobi_tb_kernel");
@@ -318,8 +327,8 @@ int tb_rows(const fluid_t* h, int W, int rows, int reserve = 0) {
     using T = TB<K>;
     const int nxw = (W + T::VALID - 1) / T::VALID;
     int occ = 0;
-    if (tb_use_tma(h)) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, jacobi_tb_kernel<K, false, true>, 32, T::SMEM_TMA);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, jacobi_tb_kernel<K, false, false>, 32, T::SMEM_LDGSTS);
+    if (tb_use_tma(h)) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, jacobi_tb_kernel<K, false, true, false>, 32, T::SMEM_TMA);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, jacobi_tb_kernel<K, false, false, false>, 32, T::SMEM_LDGSTS);
     if (occ < 1) occ = 1;
     if (h->jacobi_warps_per_sm > 0) occ = std::min(occ, h->jacobi_warps_per_sm);
     const int resident_warps = std::max(nxw, h->sm_count * occ - reserve);
@@ -482,32 +491,33 @@ int run_jacobi(fluid_t* h, int iters, bool scale_first, int* launches_out) {
             }
             a.out_lo = std::max(h->row0 - ext, 0); a.out_hi = std::min(h->row1 + ext, H);
         }
-        a.sy = TbSync{};
+        h->tb_sync = TbSync{}; h->tb_sync_on = false;
         if (mirror) {
             const unsigned seq = h->mir_seq + 1;
+            h->tb_sync_on = (k == 0 && p_in_place) || k == nlaunch - 2 || last;
             if (k == 0 && p_in_place) {                          // wait for the previous solve's mirrored rows
                 for (int s = 0; s < 2; ++s)
-                    if (h->peer[s].present) a.sy.pre_wait[s] = my_flags + 66 + s;
-                a.sy.pre_seq = h->mir_seq; a.sy.own_lo = h->row0; a.sy.own_hi = h->row1;
+                    if (h->peer[s].present) h->tb_sync.pre_wait[s] = my_flags + 66 + s;
+                h->tb_sync.pre_seq = h->mir_seq; h->tb_sync.own_lo = h->row0; h->tb_sync.own_hi = h->row1;
             }
             if (k == nlaunch - 2) {                              // last reader of the ghost rows the neighbours will overwrite
-                a.sy.ticket = my_flags + 72;
+                h->tb_sync.ticket = my_flags + 72;
                 for (int s = 0; s < 2; ++s)
-                    if (h->peer[s].present) a.sy.done_flag[s] = peer_flags(s) + (s == 0 ? 65 : 64);
-                a.sy.done_seq = seq;
+                    if (h->peer[s].present) h->tb_sync.done_flag[s] = peer_flags(s) + (s == 0 ? 65 : 64);
+                h->tb_sync.done_seq = seq;
             }
             if (last) {
                 const int pidx = ((char*)h->pressure.write == h->arena + h->off_p[0]) ? 0 : 1;
                 for (int s = 0; s < 2; ++s) {
                     const fluid::Peer& P = h->peer[s];
                     if (!P.present) continue;
-                    a.sy.mirror[s] = (float*)(P.base + P.off_p[pidx]) - (ptrdiff_t)P.roff * W;
-                    a.sy.mir_lo[s] = s == 0 ? h->row0 : h->row1 - (iters + 1);
-                    a.sy.mir_hi[s] = s == 0 ? h->row0 + (iters + 1) : h->row1;
-                    a.sy.mir_wait[s] = my_flags + 64 + s;
-                    a.sy.done_flag[s] = peer_flags(s) + (s == 0 ? 67 : 66);
+                    h->tb_sync.mirror[s] = (float*)(P.base + P.off_p[pidx]) - (ptrdiff_t)P.roff * W;
+                    h->tb_sync.mir_lo[s] = s == 0 ? h->row0 : h->row1 - (iters + 1);
+                    h->tb_sync.mir_hi[s] = s == 0 ? h->row0 + (iters + 1) : h->row1;
+                    h->tb_sync.mir_wait[s] = my_flags + 64 + s;
+                    h->tb_sync.done_flag[s] = peer_flags(s) + (s == 0 ? 67 : 66);
                 }
-                a.sy.mir_seq = seq; a.sy.ticket = my_flags + 73; a.sy.done_seq = seq;
+                h->tb_sync.mir_seq = seq; h->tb_sync.ticket = my_flags + 73; h->tb_sync.done_seq = seq;
             }
         }
         const bool sc = scale_first && k == 0;
@@ -533,7 +543,7 @@ int run_jacobi(fluid_t* h, int iters, bool scale_first, int* launches_out) {
         } else if (blocked) {
             h->pdl_chain = (k > 0) && !(overlap && k == 1);   // directly behind another blocked launch on this stream
             rc = launch_tb_dyn(h, K, a, sc);
-            h->pdl_chain = false;
+            h->pdl_chain = false; h->tb_sync_on = false;
         } else if (tb_eligible(h)) {
             dim3 b(32, 8);
             dim3 g((W / 4 + b.x - 1) / b.x, (a.out_hi - a.out_lo + b.y - 1) / b.y);

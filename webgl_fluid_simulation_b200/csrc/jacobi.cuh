@@ -88,8 +88,14 @@ struct JacobiArgs {
     // wait for the halo while the interior runs): chunks 0..nch1-1 tile [out_lo, out_hi), the rest
     // tile [seg2_lo, seg2_hi).  nch1 <= 0: single range.
     int nch1, seg2_lo, seg2_hi;
-    TbSync sy;
 };
+// kernel argument block: the hand-offs exist only in the SYNC instantiation.  The single-GPU kernel must
+// not pay for slab plumbing: with TbSync inside JacobiArgs and the null checks compiled into the one
+// kernel, the 4096^2 solve measured 3 % slower (profiles/r02_scaling.md).  (A derived struct, not a
+// separate kernel parameter: with the latter ptxas gave up the converged-warp assumption of the hot
+// loops — shuffles with BRA.DIV scaffolding, a fifth copy of the block body.)
+template <bool SYNC> struct TbArgs : JacobiArgs {};
+template <> struct TbArgs<true> : JacobiArgs { TbSync sy; };
 
 // the two tensor maps a temporally blocked launch reads through (TMA staging); 64-byte aligned
 // CUtensorMap images, passed by value as a __grid_constant__ kernel parameter
@@ -558,39 +564,45 @@ __device__ __forceinline__ void st_v4_if(float4* p, const float4 v, const bool o
     asm volatile("{ .reg .pred q; setp.ne.u32 q, %5, 0; @q st.global.v4.f32 [%0], {%1, %2, %3, %4}; }"
                  ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"((unsigned)on) : "memory");
 }
-__device__ __forceinline__ void tb_mirror(const JacobiArgs& a, const int gx, const bool lane_out, const int y0, const int y1) {
+__device__ __forceinline__ void tb_mirror(const JacobiArgs& a, const TbSync& sy, const int gx, const bool lane_out, const int y0, const int y1) {
     const int W4 = a.W >> 2;
     const int col = lane_out ? (gx >> 2) : 0;
     const float4* own = reinterpret_cast<const float4*>(a.pout) - (ptrdiff_t)a.row_off * W4 + col;
 #pragma unroll 1
     for (int s = 0; s < 2; ++s) {
-        if (a.sy.mirror[s] == nullptr) continue;
-        const int lo = max(y0, a.sy.mir_lo[s]), hi = min(y1, a.sy.mir_hi[s]);
+        if (sy.mirror[s] == nullptr) continue;
+        const int lo = max(y0, sy.mir_lo[s]), hi = min(y1, sy.mir_hi[s]);
         if (lo >= hi) continue;
-        spin_until(a.sy.mir_wait[s], a.sy.mir_seq, a.err);          // every lane polls the same word: uniform
-        float4* dst = reinterpret_cast<float4*>(a.sy.mirror[s]) + col;
+        spin_until(sy.mir_wait[s], sy.mir_seq, a.err);          // every lane polls the same word: uniform
+        float4* dst = reinterpret_cast<float4*>(sy.mirror[s]) + col;
 #pragma unroll 4
         for (int r = lo; r < hi; ++r) st_v4_if(dst + (ptrdiff_t)r * W4, own[(ptrdiff_t)r * W4], lane_out);
+        // this lane's stores are performed at the neighbour before the lane goes on to the completion ticket.
+        // (fence.acq_rel, not __threadfence_system(): that one is fence.sc — MEMBAR.SC.SYS, totally ordered
+        // among ALL the grid's warps — and measured 35 us per solve when every warp issued it)
+        asm volatile("fence.acq_rel.sys;" ::: "memory");
     }
-    __threadfence_system();
 }
 
 // Grid-completion signal: the last CTA to get here release-stores done_seq into the neighbours' words.
-__device__ __forceinline__ void tb_signal_done(const JacobiArgs& a, const int lane) {
-    __threadfence_system();
-    // every lane is past its fence before lane 0 takes the ticket (a vote, not __syncwarp: see above)
+__device__ __forceinline__ void tb_signal_done(const TbSync& sy, const int lane) {
+    // every lane is past its stores (and, in tb_mirror, its fence) before lane 0 takes the ticket — a vote,
+    // not __syncwarp: see above.  The ticket is a release at GPU scope; the last CTA's fence + release-store
+    // at system scope then publishes everything that happened before any ticket.
     const unsigned first = (__all_sync(0xffffffffu, 1) && lane == 0) ? 1u : 0u;
     unsigned t;
-    asm volatile("{ .reg .pred q; setp.ne.u32 q, %1, 0; mov.u32 %0, 0xffffffff; @q atom.global.add.u32 %0, [%2], 1; }"
-                 : "=r"(t) : "r"(first), "l"(a.sy.ticket) : "memory");
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %1, 0; mov.u32 %0, 0xffffffff; @q atom.acq_rel.gpu.global.add.u32 %0, [%2], 1; }"
+                 : "=r"(t) : "r"(first), "l"(sy.ticket) : "memory");
     const unsigned last = (t == gridDim.x - 1) ? 1u : 0u;              // lane 0 of the last CTA only
-    asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q st.global.u32 [%1], 0; @q fence.acq_rel.sys; }"
-                 ::"r"(last), "l"(a.sy.ticket) : "memory");
+    if (__any_sync(0xffffffffu, last)) {                               // warp-uniform branch: one CTA of the grid enters
+        asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q st.global.u32 [%1], 0; @q fence.acq_rel.sys; }"
+                     ::"r"(last), "l"(sy.ticket) : "memory");
 #pragma unroll
-    for (int s = 0; s < 2; ++s) {
-        if (a.sy.done_flag[s] == nullptr) continue;
-        asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q st.release.sys.global.u32 [%1], %2; }"
-                     ::"r"(last), "l"(a.sy.done_flag[s]), "r"(a.sy.done_seq) : "memory");
+        for (int s = 0; s < 2; ++s) {
+            if (sy.done_flag[s] == nullptr) continue;
+            asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q st.release.sys.global.u32 [%1], %2; }"
+                         ::"r"(last), "l"(sy.done_flag[s]), "r"(sy.done_seq) : "memory");
+        }
     }
 }
 
@@ -605,8 +617,8 @@ __device__ __forceinline__ void tb_signal_done(const JacobiArgs& a, const int la
 #else
 #define FLUID_TB_BOUNDS __launch_bounds__(32, FLUID_TB_MINBLOCKS)
 #endif
-template <int K, bool SCALE, bool TMA>
-__global__ void FLUID_TB_BOUNDS jacobi_tb_kernel(JacobiArgs a, const __grid_constant__ TmapPair maps) {
+template <int K, bool SCALE, bool TMA, bool SYNC>
+__global__ void FLUID_TB_BOUNDS jacobi_tb_kernel(TbArgs<SYNC> a, const __grid_constant__ TmapPair maps) {
     using T = TB<K>;
     extern __shared__ __align__(128) float4 smem4[];
     // Programmatic dependent launch: back-to-back blocked launches of one solve are chained with
@@ -645,8 +657,11 @@ __global__ void FLUID_TB_BOUNDS jacobi_tb_kernel(JacobiArgs a, const __grid_cons
     // slab, first launch of a solve whose pressure ghost rows were stored by the neighbours' previous
     // last launch: the streams that read those rows acquire "mirror ready" first
     // (every lane polls the same word — warp-uniform control flow, see tb_mirror)
-    if (a.sy.pre_wait[0] != nullptr && ys < a.sy.own_lo) spin_until(a.sy.pre_wait[0], a.sy.pre_seq, a.err);
-    if (a.sy.pre_wait[1] != nullptr && ye >= a.sy.own_hi) spin_until(a.sy.pre_wait[1], a.sy.pre_seq, a.err);
+    if constexpr (SYNC) {
+        const TbSync& sy = a.sy;
+        if (sy.pre_wait[0] != nullptr && ys < sy.own_lo) spin_until(sy.pre_wait[0], sy.pre_seq, a.err);
+        if (sy.pre_wait[1] != nullptr && ye >= sy.own_hi) spin_until(sy.pre_wait[1], sy.pre_seq, a.err);
+    }
 
     // ---- does the divergence this stream reads hold a value that defeats the fma contraction? ----
     bool exact = false;
@@ -672,8 +687,11 @@ __global__ void FLUID_TB_BOUNDS jacobi_tb_kernel(JacobiArgs a, const __grid_cons
     } else {
         tb_stream_exact<K, SCALE, TMA>(a, tp, td, smem4, lane, x0, lc, gx, rev, lane_out, y0, y1, ys, ye, any_rev);
     }
-    if (a.sy.mirror[0] != nullptr || a.sy.mirror[1] != nullptr) tb_mirror(a, gx, lane_out, y0, y1);
-    if (a.sy.ticket != nullptr) tb_signal_done(a, lane);
+    if constexpr (SYNC) {
+        const TbSync& sy = a.sy;
+        if (sy.mirror[0] != nullptr || sy.mirror[1] != nullptr) tb_mirror(a, sy, gx, lane_out, y0, y1);
+        if (sy.ticket != nullptr) tb_signal_done(sy, lane);
+    }
 }
 
 // ---- producers of the tiny-divergence map ----------------------------------------------------------
