@@ -330,6 +330,31 @@ def test_host_pressure_solve_matches_resident_path(pkg):
     s.close()
 
 
+@pytest.mark.parametrize("W,H,iters", [(1024, 2048, 50), (256, 1000, 20), (4096, 4096, 50)])
+def test_host_pressure_solve_banded_pipeline(pkg, W, H, iters):
+    """fluid_pressure_solve_host cuts the grid into row bands and solves each behind the copies
+    (fluid.cu solve_host_banded): same bits as the resident one-piece solve, result also left in the
+    device field, tiny divergence values (un-contracted instantiation) included, ragged last band."""
+    rng = np.random.default_rng(5)
+    p = rng.standard_normal((H, W)).astype(np.float32)
+    d = rng.uniform(-1, 1, (H, W)).astype(np.float32)
+    d[H // 3, W // 5] = np.float32(2.0 ** -130)            # defeats the fma contraction: flagged through the scan of the band
+    d[H - 7, 3] = np.float32(-2.0 ** -140)
+    s = make(pkg, W, H, 64, 64, PRESSURE_ITERATIONS=iters)
+    s.writeField("pressure", p); s.writeField("divergence", d)
+    s.pass_("pressure_solve"); a = s.readField("pressure")
+    ph = p.copy()
+    s.pressure_solve_host(d, ph, iters)
+    assert bits_equal(a, ph)
+    assert bits_equal(s.readField("pressure"), ph)
+    assert bits_equal(s.readField("divergence"), d)
+    ph2 = ph.copy()
+    s.pressure_solve_host(d, ph2, iters)                   # a second call (ping-pong parity flipped, private rows reused)
+    s.writeField("pressure", ph); s.pass_("pressure_solve")
+    assert bits_equal(s.readField("pressure"), ph2)
+    s.close()
+
+
 def test_resize_carries_state_like_resizeDoubleFBO(pkg, oracle):
     O = oracle
     v, dye, p = rand_fields(32, 32, 64, 64, 9)

@@ -101,6 +101,14 @@ struct fluid {
     uint32_t mir_seq = 0;
     bool p_mirror_valid = false;
     int p_mirror_rows = 0;
+    // fluid_pressure_solve_host pipelined over row bands (single GPU): copy streams, per-band events and the
+    // band-private ping-pong rows of the intermediate launches
+    struct HostPipe {
+        cudaStream_t up = nullptr, down = nullptr;
+        cudaEvent_t ev_start = nullptr, ev_up[16] = {}, ev_done[16] = {};
+        float* s[2] = {nullptr, nullptr};
+        size_t s_floats = 0;
+    } hp;
     fk::TbSync tb_sync{};                      // hand-offs of the NEXT blocked launch (launch_tb: SYNC instantiation when tb_sync_on)
     bool tb_sync_on = false;
     // divergence ghost rows of the exchange about to be issued: the peer-memory wait kernel scans them (halo.cuh)
@@ -287,6 +295,8 @@ int launch_tb(fluid_t* h, const JacobiArgs& a) {
     // chained to the previous launch of the same solve by programmatic dependent launch (jacobi.cuh);
     // not while a graph is being captured, FLUID_PDL=0 turns it off
     static const bool pdl_off = getenv("FLUID_PDL") && !strcmp(getenv("FLUID_PDL"), "0");
+    // tuning: run the SYNC instantiation everywhere (all hand-offs null) to time it against the plain one
+    static const bool force_sync = getenv("FLUID_TB_FORCE_SYNC") && !strcmp(getenv("FLUID_TB_FORCE_SYNC"), "1");
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -301,7 +311,7 @@ int launch_tb(fluid_t* h, const JacobiArgs& a) {
         memcpy(maps.d, &h->tmaps.d, sizeof(CUtensorMap));
         lc.dynamicSmemBytes = T::SMEM_TMA;
         { TbArgs<false> ta; static_cast<JacobiArgs&>(ta) = a; cudaLaunchKernelEx(&lc, jacobi_tb_kernel<K, SCALE, true, false>, ta, maps); }   // one warp per CTA
-    } else if (h->tb_sync_on) {                       // slab launch with hand-offs (run_jacobi fills h->tb_sync)
+    } else if (h->tb_sync_on || force_sync) {         // slab launch with hand-offs (run_jacobi fills h->tb_sync)
         lc.dynamicSmemBytes = T::SMEM_LDGSTS;
         TbArgs<true> ta; static_cast<JacobiArgs&>(ta) = a; ta.sy = h->tb_sync;
         cudaLaunchKernelEx(&lc, jacobi_tb_kernel<K, SCALE, false, true>, ta, maps);
@@ -541,7 +551,10 @@ int run_jacobi(fluid_t* h, int iters, bool scale_first, int* launches_out) {
             if (rc) return rc;
             CU(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
         } else if (blocked) {
-            h->pdl_chain = (k > 0) && !(overlap && k == 1);   // directly behind another blocked launch on this stream
+            // programmatic dependent launch: behind another blocked launch of this solve, and — first launch —
+            // behind whatever kernel precedes it on the stream (the previous solve's last launch in a host loop
+            // of solves; a kernel without griddepcontrol.launch_dependents simply triggers at its end)
+            h->pdl_chain = !(overlap && k <= 1);
             rc = launch_tb_dyn(h, K, a, sc);
             h->pdl_chain = false; h->tb_sync_on = false;
         } else if (tb_eligible(h)) {
@@ -900,6 +913,12 @@ void fluid_destroy(fluid_t* h) {
     if (h->comm) { ncdl::api().CommDestroy(h->comm); h->comm = nullptr; }
     for (auto& e : h->mark) if (e) cudaEventDestroy(e);
     for (auto& e : h->tev) if (e) cudaEventDestroy(e);
+    if (h->hp.up) { cudaStreamSynchronize(h->hp.up); cudaStreamDestroy(h->hp.up); }
+    if (h->hp.down) { cudaStreamSynchronize(h->hp.down); cudaStreamDestroy(h->hp.down); }
+    if (h->hp.ev_start) cudaEventDestroy(h->hp.ev_start);
+    for (auto& e : h->hp.ev_up) if (e) cudaEventDestroy(e);
+    for (auto& e : h->hp.ev_done) if (e) cudaEventDestroy(e);
+    cudaFree(h->hp.s[0]); cudaFree(h->hp.s[1]);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
@@ -1515,6 +1534,86 @@ int fluid_write(fluid_t* h, int field, const float* host, size_t n_floats) {
     return FLUID_OK;
 }
 
+// fluid_pressure_solve_host on one GPU is PCIe-bound (4096^2: 128 MiB up, 64 MiB down, 3.7 of its 3.96 ms), so
+// the solve is hidden behind the copies: the grid is cut into row bands, band b is solved as soon as its rows
+// (+ `iters` rows beyond it) have arrived and is copied back while the later bands still upload — the slab
+// decomposition of section 7 applied in time instead of across GPUs, the host standing in for the
+// neighbours.  Communication-avoiding schedule as on a slab: launch k of a band produces its rows +- (sweeps
+// still to come), out of band-private ping-pong rows; the first launch reads the uploaded field, the last one
+// writes the band's rows of the result field.  Bit-identical to the one-piece solve (same kernel, same
+// per-cell arithmetic; which rows a launch covers does not enter the values).
+int solve_host_banded(fluid_t* h, const float* div_host, float* p_host, int iters, int nb) {
+    const int W = h->cfg.sim_w, H = h->cfg.sim_h;
+    fluid::HostPipe& hp = h->hp;
+    if (!hp.up) {
+        CU(cudaStreamCreateWithFlags(&hp.up, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&hp.down, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&hp.ev_start, cudaEventDisableTiming));
+        for (auto& e : hp.ev_up) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto& e : hp.ev_done) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    int kb = h->cfg.jacobi_block > 0 ? h->cfg.jacobi_block : 10;
+    kb = std::min(kb, KMAX);
+    const int nlaunch = (iters + kb - 1) / kb;
+    const int base = iters / nlaunch, extra = iters % nlaunch;
+    const int band = (H + nb - 1) / nb, halo = iters;
+    const size_t need = (size_t)(band + 2 * halo) * W;
+    if (hp.s_floats < need) {
+        cudaFree(hp.s[0]); cudaFree(hp.s[1]); hp.s[0] = hp.s[1] = nullptr; hp.s_floats = 0;
+        CU(cudaMalloc((void**)&hp.s[0], need * sizeof(float)));
+        CU(cudaMalloc((void**)&hp.s[1], need * sizeof(float)));
+        hp.s_floats = need;
+    }
+    float* const p_in = (float*)h->pressure.read;
+    float* const result = (float*)h->pressure.write;
+    h->p_mirror_valid = false;
+    int rc = clear_tiny_map(h); if (rc) return rc;
+    CU(cudaEventRecord(hp.ev_start, h->stream));          // the copies overwrite fields earlier work on the stream may still read
+    CU(cudaStreamWaitEvent(hp.up, hp.ev_start, 0));
+    for (int b = 0; b < nb; ++b) {
+        const int b_lo = std::min(b * band, H), b_hi = std::min(b_lo + band, H);
+        if (b_hi <= b_lo) break;
+        // upload chunk b = what band b needs beyond what the earlier chunks brought: rows up to b_hi + halo
+        const int up_lo = b == 0 ? 0 : std::min(b_lo + halo, H), up_hi = (b_hi == H) ? H : std::min(b_hi + halo, H);
+        if (up_hi > up_lo) {
+            const size_t o = (size_t)up_lo * W, n = (size_t)(up_hi - up_lo) * W * sizeof(float);
+            CU(cudaMemcpyAsync(h->divergence + o, div_host + o, n, cudaMemcpyHostToDevice, hp.up));
+            CU(cudaMemcpyAsync(p_in + o, p_host + o, n, cudaMemcpyHostToDevice, hp.up));
+        }
+        CU(cudaEventRecord(hp.ev_up[b], hp.up));
+        CU(cudaStreamWaitEvent(h->stream, hp.ev_up[b], 0));
+        if ((rc = scan_tiny(h, up_lo, up_hi))) return rc;
+        const int loc = b_lo - halo;                      // global row of local row 0 of the band-private rows (may be < 0)
+        int remaining = iters;
+        for (int k = 0; k < nlaunch; ++k) {
+            const int K = base + (k < extra ? 1 : 0);
+            const bool last = (k == nlaunch - 1);
+            remaining -= K;
+            JacobiArgs a{};
+            a.W = W; a.H = H; a.scale = h->cfg.pressure; a.err = h->halo_flag; a.tiny_map = h->tiny_map;
+            a.out_lo = std::max(b_lo - remaining, 0); a.out_hi = std::min(b_hi + remaining, H);
+            // the kernel addresses all three fields as "local row 0 + (row - row_off)": a whole-grid field G is
+            // passed as G + loc*W (only rows inside the grid are ever dereferenced)
+            a.row_off = loc;
+            a.div = h->divergence + (ptrdiff_t)loc * W;
+            a.pin = (k == 0) ? p_in + (ptrdiff_t)loc * W : hp.s[(k - 1) & 1];
+            a.pout = last ? result + (ptrdiff_t)loc * W : hp.s[k & 1];
+            h->pdl_chain = (k > 0);
+            rc = launch_tb_dyn(h, K, a, k == 0);
+            h->pdl_chain = false;
+            if (rc) return rc;
+        }
+        CU(cudaEventRecord(hp.ev_done[b], h->stream));
+        CU(cudaStreamWaitEvent(hp.down, hp.ev_done[b], 0));
+        const size_t o = (size_t)b_lo * W;
+        CU(cudaMemcpyAsync(p_host + o, result + o, (size_t)(b_hi - b_lo) * W * sizeof(float), cudaMemcpyDeviceToHost, hp.down));
+    }
+    swap_p(h);                                            // pressure.read = the result, like S:1265 after the loop
+    CU(cudaStreamSynchronize(hp.down));
+    CU(cudaStreamSynchronize(h->stream));
+    return FLUID_OK;
+}
+
 int fluid_pressure_solve_host(fluid_t* h, const float* div_host, float* p_host, int iters) {
     if (!h || !div_host || !p_host || iters < 0) return fail(h, FLUID_ERR_INVALID, "bad argument");
     if (h->half) {
@@ -1523,6 +1622,12 @@ int fluid_pressure_solve_host(fluid_t* h, const float* div_host, float* p_host, 
         if (!rc) rc = run_jacobi(h, iters, true, nullptr);
         if (!rc) rc = fluid_read(h, FLUID_FIELD_PRESSURE, p_host, (size_t)h->cfg.sim_w * h->cfg.sim_h);
         return rc;
+    }
+    // one GPU, blocked kernel: solve band by band behind the copies (FLUID_E2E_BANDS=1 keeps the one-piece path)
+    if (!h->slab() && iters > 0 && tb_eligible(h) && !(h->cfg.flags & FLUID_FLAG_NAIVE_JACOBI) && h->cfg.jacobi_block != 1 && !tb_use_tma(h)) {
+        static const int bands_env = getenv("FLUID_E2E_BANDS") ? atoi(getenv("FLUID_E2E_BANDS")) : 8;
+        int nb = std::min(std::min(bands_env, 16), h->cfg.sim_h / std::max(256, 4 * iters));
+        if (nb >= 2) return solve_host_banded(h, div_host, p_host, iters, nb);
     }
     const size_t n = (size_t)h->cfg.sim_w * (h->row1 - h->row0);   // owned rows
     const size_t go = (size_t)h->G * h->cfg.sim_w;

@@ -575,8 +575,16 @@ __device__ __forceinline__ void tb_mirror(const JacobiArgs& a, const TbSync& sy,
         if (lo >= hi) continue;
         spin_until(sy.mir_wait[s], sy.mir_seq, a.err);          // every lane polls the same word: uniform
         float4* dst = reinterpret_cast<float4*>(sy.mirror[s]) + col;
-#pragma unroll 4
-        for (int r = lo; r < hi; ++r) st_v4_if(dst + (ptrdiff_t)r * W4, own[(ptrdiff_t)r * W4], lane_out);
+        // 16 rows at a time: all the loads first (the stores are volatile asm, nothing moves across them —
+        // one load -> store pair per row was a chain of ~50 L2 round trips, 35 us per solve)
+#pragma unroll 1
+        for (int r = lo; r < hi; r += 16) {
+            float4 v[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[q] = own[(ptrdiff_t)min(r + q, hi - 1) * W4];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) st_v4_if(dst + (ptrdiff_t)min(r + q, hi - 1) * W4, v[q], lane_out);   // the last row may be stored twice
+        }
         // this lane's stores are performed at the neighbour before the lane goes on to the completion ticket.
         // (fence.acq_rel, not __threadfence_system(): that one is fence.sc — MEMBAR.SC.SYS, totally ordered
         // among ALL the grid's warps — and measured 35 us per solve when every warp issued it)

@@ -105,8 +105,14 @@ __global__ void __launch_bounds__(32 * GS_WARPS) gradient_stream_kernel(const fl
 // warp produce output, 120 columns.
 constexpr int CVD2_WARPS = 4;
 constexpr int CVD2_VALID = 120;
-constexpr int CVD2_MINBLOCKS = 5;                                // register budget: 5 CTAs = 20 streams per SM
-constexpr int CVD2_RING = 6;                                     // rows in flight per warp (1 KB each)
+#ifndef FLUID_CVD_MINBLOCKS            // tuning builds
+#define FLUID_CVD_MINBLOCKS 5
+#endif
+#ifndef FLUID_CVD_RING
+#define FLUID_CVD_RING 6
+#endif
+constexpr int CVD2_MINBLOCKS = FLUID_CVD_MINBLOCKS;              // register budget: 5 CTAs = 20 streams per SM
+constexpr int CVD2_RING = FLUID_CVD_RING;                        // rows in flight per warp (1 KB each)
 constexpr int CVD2_SMEM = CVD2_WARPS * CVD2_RING * 64 * (int)sizeof(float4);
 
 struct Vel4 { float x[4], y[4]; };          // 4 consecutive cells of a velocity row
