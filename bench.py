@@ -465,7 +465,7 @@ def main():
     out["e2e"] = {"value": W * H * ITERS * e_steps * world / e_dt, "unit": UNIT,
                   "h2d_bytes_per_step": 2 * W * H * 4 * world, "d2h_bytes_per_step": W * H * 4 * world,
                   "ms_per_step": 1e3 * e_dt / e_steps, "steps": e_steps,
-                  "api": "fluid_pressure_solve_host (pinned host buffers; H2D div+p, solve, D2H p; per rank: its slab)"}
+                  "api": "fluid_pressure_solve_host (pinned host buffers; H2D div+p, solve, D2H p, all inside the call; one GPU: row bands solved and downloaded behind the upload; per rank: its slab)"}
     del ph, dh
 
     # ---- strong scaling of the headline grid (north_star: "1/2/4/8 B200 on a 4096^2 grid") ----------

@@ -505,10 +505,13 @@ int run_jacobi(fluid_t* h, int iters, bool scale_first, int* launches_out) {
         if (mirror) {
             const unsigned seq = h->mir_seq + 1;
             h->tb_sync_on = (k == 0 && p_in_place) || k == nlaunch - 2 || last;
+            static const bool dbg = getenv("FLUID_DEBUG_HALO_TIMING") != nullptr;
+            if (dbg) h->tb_sync.dbg = (unsigned long long*)(h->arena + h->off_flags + 512);
+            h->tb_sync.own_lo = h->row0; h->tb_sync.own_hi = h->row1;
             if (k == 0 && p_in_place) {                          // wait for the previous solve's mirrored rows
                 for (int s = 0; s < 2; ++s)
                     if (h->peer[s].present) h->tb_sync.pre_wait[s] = my_flags + 66 + s;
-                h->tb_sync.pre_seq = h->mir_seq; h->tb_sync.own_lo = h->row0; h->tb_sync.own_hi = h->row1;
+                h->tb_sync.pre_seq = h->mir_seq;
             }
             if (k == nlaunch - 2) {                              // last reader of the ghost rows the neighbours will overwrite
                 h->tb_sync.ticket = my_flags + 72;
@@ -902,6 +905,13 @@ void fluid_destroy(fluid_t* h) {
     if (h->p2p && getenv("FLUID_DEBUG_HALO_TIMING")) {
         unsigned long long d[5] = {};
         cudaMemcpy(d, h->arena + h->off_flags + 128, sizeof d, cudaMemcpyDeviceToHost);
+        unsigned long long m[9] = {};
+        cudaMemcpy(m, h->arena + h->off_flags + 512, sizeof m, cudaMemcpyDeviceToHost);
+        if (m[6] || m[8])
+            fprintf(stderr, "[mirror rank %d] streams that waited for mirror-ready: %llu, avg %.1f us; mirroring warps: %llu, waited %.1f us for done-reading, "
+                            "copied for %.1f us; stream life (hand-off launches): %.1f us touching ghost rows (%llu), %.1f us others (%llu)\n",
+                    h->rank, m[1], m[1] ? m[0] / 1e3 / m[1] : 0.0, m[4], m[4] ? m[2] / 1e3 / m[4] : 0.0, m[4] ? m[3] / 1e3 / m[4] : 0.0,
+                    m[6] ? m[5] / 1e3 / m[6] : 0.0, m[6], m[8] ? m[7] / 1e3 / m[8] : 0.0, m[8]);
         if (d[3]) fprintf(stderr, "[halo rank %d] exchanges %llu: wait-free %.1f us, push (start->published) %.1f us, wait-ready %.1f us\n",
                           h->rank, d[3], d[0] / 1e3 / d[3], d[1] / 1e3 / d[3], d[2] / 1e3 / d[3]);
     }
@@ -1625,7 +1635,7 @@ int fluid_pressure_solve_host(fluid_t* h, const float* div_host, float* p_host, 
     }
     // one GPU, blocked kernel: solve band by band behind the copies (FLUID_E2E_BANDS=1 keeps the one-piece path)
     if (!h->slab() && iters > 0 && tb_eligible(h) && !(h->cfg.flags & FLUID_FLAG_NAIVE_JACOBI) && h->cfg.jacobi_block != 1 && !tb_use_tma(h)) {
-        static const int bands_env = getenv("FLUID_E2E_BANDS") ? atoi(getenv("FLUID_E2E_BANDS")) : 8;
+        static const int bands_env = getenv("FLUID_E2E_BANDS") ? atoi(getenv("FLUID_E2E_BANDS")) : 16;
         int nb = std::min(std::min(bands_env, 16), h->cfg.sim_h / std::max(256, 4 * iters));
         if (nb >= 2) return solve_host_banded(h, div_host, p_host, iters, nb);
     }

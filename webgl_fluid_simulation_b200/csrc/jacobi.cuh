@@ -60,6 +60,24 @@ __device__ __forceinline__ void spin_until(const unsigned* flag, unsigned seq, i
 //     sequence number into my flag word, and my mirroring warps acquire it first;
 //   * "mirror ready": my last CTA to finish release-stores the sequence number into the neighbour's
 //     flag word; the streams of its next first launch that read ghost rows acquire it first.
+// The same wait for a whole (converged, one-warp-CTA) warp: lane 0 polls, a vote carries the outcome — one
+// request per poll instead of 32, and no lane-dependent branch (see tb_mirror for why that matters here).
+// Each lane then performs its own acquire load of the flag before it touches what the flag guards.
+__device__ __forceinline__ void warp_spin_until(const unsigned* flag, unsigned seq, int* err) {
+    const unsigned long long t0 = global_ns();
+    const unsigned l0 = (threadIdx.x == 0) ? 1u : 0u;
+    for (;;) {
+        unsigned v = seq;
+        asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q ld.acquire.sys.global.u32 %0, [%1]; }" : "+r"(v) : "l"(flag), "r"(l0) : "memory");
+        if (!__any_sync(0xffffffffu, (int)(v - seq) < 0)) break;
+        if (global_ns() - t0 > 4000000000ull) { *err = 2; break; }      // all lanes agree within a poll or two; the store is idempotent
+        __nanosleep(200);
+    }
+    // every lane's own acquire of the (now satisfied) flag — not a fence: MEMBAR.SYS would first drain the rows
+    // this warp has just stored (measured: 6-22 us per mirroring warp)
+    (void)ld_acquire_sys(flag);
+}
+
 struct TbSync {
     const unsigned* pre_wait[2];   // [0] below, [1] above: streams reading rows outside [own_lo, own_hi) wait for *flag >= pre_seq
     unsigned pre_seq;
@@ -71,7 +89,14 @@ struct TbSync {
     unsigned* ticket;              // CTA completion counter (local); null: this launch signals nothing
     unsigned* done_flag[2];        // words in the neighbours' arenas that receive done_seq when the whole grid is done
     unsigned done_seq;
+    // FLUID_DEBUG_HALO_TIMING: u64 sums — [0] ns streams waited for "mirror ready", [1] such streams, [2] ns mirroring
+    // warps waited for "done reading", [3] ns they spent copying, [4] such warps, [5] / [6] ns and count of streams
+    // touching ghost rows (whole life), [7] / [8] of the other streams
+    unsigned long long* dbg;
 };
+__device__ __forceinline__ void dbg_add(unsigned long long* p, unsigned long long v, bool on) {   // predicated, no branch (see tb_mirror)
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q red.global.add.u64 [%0], %1; }" ::"l"(p), "l"(v), "r"((unsigned)on) : "memory");
+}
 
 struct JacobiArgs {
     const float* pin;    // local row 0 of the source pressure buffer
@@ -573,7 +598,9 @@ __device__ __forceinline__ void tb_mirror(const JacobiArgs& a, const TbSync& sy,
         if (sy.mirror[s] == nullptr) continue;
         const int lo = max(y0, sy.mir_lo[s]), hi = min(y1, sy.mir_hi[s]);
         if (lo >= hi) continue;
-        spin_until(sy.mir_wait[s], sy.mir_seq, a.err);          // every lane polls the same word: uniform
+        const unsigned long long t1 = sy.dbg ? global_ns() : 0ull;
+        warp_spin_until(sy.mir_wait[s], sy.mir_seq, a.err);
+        const unsigned long long t2 = sy.dbg ? global_ns() : 0ull;
         float4* dst = reinterpret_cast<float4*>(sy.mirror[s]) + col;
         // 16 rows at a time: all the loads first (the stores are volatile asm, nothing moves across them —
         // one load -> store pair per row was a chain of ~50 L2 round trips, 35 us per solve)
@@ -589,6 +616,11 @@ __device__ __forceinline__ void tb_mirror(const JacobiArgs& a, const TbSync& sy,
         // (fence.acq_rel, not __threadfence_system(): that one is fence.sc — MEMBAR.SC.SYS, totally ordered
         // among ALL the grid's warps — and measured 35 us per solve when every warp issued it)
         asm volatile("fence.acq_rel.sys;" ::: "memory");
+        if (sy.dbg) {
+            const unsigned long long t3 = global_ns();
+            const bool l0 = (threadIdx.x == 0);
+            dbg_add(sy.dbg + 2, t2 - t1, l0); dbg_add(sy.dbg + 3, t3 - t2, l0); dbg_add(sy.dbg + 4, 1ull, l0);
+        }
     }
 }
 
@@ -665,10 +697,14 @@ __global__ void FLUID_TB_BOUNDS jacobi_tb_kernel(TbArgs<SYNC> a, const __grid_co
     // slab, first launch of a solve whose pressure ghost rows were stored by the neighbours' previous
     // last launch: the streams that read those rows acquire "mirror ready" first
     // (every lane polls the same word — warp-uniform control flow, see tb_mirror)
+    unsigned long long t_start = 0;
     if constexpr (SYNC) {
         const TbSync& sy = a.sy;
-        if (sy.pre_wait[0] != nullptr && ys < sy.own_lo) spin_until(sy.pre_wait[0], sy.pre_seq, a.err);
-        if (sy.pre_wait[1] != nullptr && ye >= sy.own_hi) spin_until(sy.pre_wait[1], sy.pre_seq, a.err);
+        if (sy.dbg) t_start = global_ns();
+        const bool w0 = sy.pre_wait[0] != nullptr && ys < sy.own_lo, w1 = sy.pre_wait[1] != nullptr && ye >= sy.own_hi;
+        if (w0) warp_spin_until(sy.pre_wait[0], sy.pre_seq, a.err);
+        if (w1) warp_spin_until(sy.pre_wait[1], sy.pre_seq, a.err);
+        if (sy.dbg && (w0 || w1)) { dbg_add(sy.dbg + 0, global_ns() - t_start, lane == 0); dbg_add(sy.dbg + 1, 1ull, lane == 0); }
     }
 
     // ---- does the divergence this stream reads hold a value that defeats the fma contraction? ----
@@ -697,6 +733,10 @@ __global__ void FLUID_TB_BOUNDS jacobi_tb_kernel(TbArgs<SYNC> a, const __grid_co
     }
     if constexpr (SYNC) {
         const TbSync& sy = a.sy;
+        if (sy.dbg) {
+            const bool edge = (ys < sy.own_lo) || (ye >= sy.own_hi);
+            dbg_add(sy.dbg + (edge ? 5 : 7), global_ns() - t_start, lane == 0); dbg_add(sy.dbg + (edge ? 6 : 8), 1ull, lane == 0);
+        }
         if (sy.mirror[0] != nullptr || sy.mirror[1] != nullptr) tb_mirror(a, sy, gx, lane_out, y0, y1);
         if (sy.ticket != nullptr) tb_signal_done(sy, lane);
     }

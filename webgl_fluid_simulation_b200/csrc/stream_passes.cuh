@@ -106,12 +106,12 @@ __global__ void __launch_bounds__(32 * GS_WARPS) gradient_stream_kernel(const fl
 constexpr int CVD2_WARPS = 4;
 constexpr int CVD2_VALID = 120;
 #ifndef FLUID_CVD_MINBLOCKS            // tuning builds
-#define FLUID_CVD_MINBLOCKS 5
+#define FLUID_CVD_MINBLOCKS 4
 #endif
 #ifndef FLUID_CVD_RING
 #define FLUID_CVD_RING 6
 #endif
-constexpr int CVD2_MINBLOCKS = FLUID_CVD_MINBLOCKS;              // register budget: 5 CTAs = 20 streams per SM
+constexpr int CVD2_MINBLOCKS = FLUID_CVD_MINBLOCKS;              // register budget: 4 CTAs = 16 streams per SM at 118 registers (5 / 6 CTAs: 5 % / 16 % slower, profiles/r02_cvd_occupancy.md)
 constexpr int CVD2_RING = FLUID_CVD_RING;                        // rows in flight per warp (1 KB each)
 constexpr int CVD2_SMEM = CVD2_WARPS * CVD2_RING * 64 * (int)sizeof(float4);
 
