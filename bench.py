@@ -99,10 +99,12 @@ def peak_hbm():
 class ClockSampler:
     """Polls NVML for SM clock + throttle reasons while the timed region runs."""
 
-    def __init__(self, index):
+    def __init__(self, index, enabled=True):
         self.samples, self.reasons, self._stop = [], set(), threading.Event()
         self.max_mhz = None
         try:
+            if not enabled:
+                raise RuntimeError("not the reporting rank")
             import pynvml as nv
             nv.nvmlInit()
             self.nv, self.h = nv, nv.nvmlDeviceGetHandleByIndex(index)
@@ -142,6 +144,9 @@ class ClockSampler:
         self._stop.set()
         if self.nv:
             self.t.join(timeout=1)
+
+    def reset(self):
+        self.samples = []; self.reasons = set()
 
     def summary(self):
         if not self.samples:
@@ -248,7 +253,13 @@ def workload_config(world, transport, strong):
 HOST_MS = {}
 
 
-def time_steps(sim, fn, steps, tag=None):
+def time_steps(sim, fn, steps, tag=None, align=False):
+    # align (N>1): one untimed solve between the barrier and the start event.  A solve on slabs is a collective
+    # between neighbours, so it lines the ranks up ON THE DEVICE: host-side skew after the barrier (a process
+    # that gets the CPU a few milliseconds late) would otherwise sit inside its neighbours' device timers, as
+    # they spin in the halo exchange waiting for it (seen at N=8: a constant 40-75 ms per run, whatever --steps).
+    if align:
+        fn()
     sim.mark(0)
     t0 = time.perf_counter()
     for _ in range(steps):
@@ -307,7 +318,9 @@ def main():
         if world == 1:
             return pkg.FluidSimulation(cfg, 1024, 1024, device=local, flags=flags, jacobi_block=jb)
         return create_slab_simulation(cfg, 1024, 1024, device=local, flags=flags, jacobi_block=jb,
-                                      sizes=(W, rows_per_rank * world, 64, 64 * world))
+                                      # the (unused) dye grid is tiny; its rows per rank bound the ghost zone, which must
+                                      # hold ITERS + 2 rows for the one-exchange-per-solve schedule
+                                      sizes=(W, rows_per_rank * world, 64, max(64, ITERS + 2) * world))
 
     sim = make_sim()
     transport = getattr(sim, "halo_transport", None)
@@ -363,11 +376,15 @@ def main():
 
     load(sim)
     solve = lambda: sim.pass_("pressure_solve")
-    for _ in range(args.warmup):
-        solve()
-    barrier()
-    with ClockSampler(local) as clk:
-        ms = time_steps(sim, solve, args.steps, tag="solve")
+    # NVML is initialised (and its polling thread started) BEFORE the warm-up and the barrier: nvmlInit with 8
+    # processes on one box takes milliseconds, which must not sit between the barrier and the timed region.
+    # Only rank 0 reports clocks, so only rank 0 polls.
+    with ClockSampler(local, enabled=(rank == 0)) as clk:
+        for _ in range(args.warmup):
+            solve()
+        barrier()
+        clk.reset()                       # keep only the samples taken during the timed region
+        ms = time_steps(sim, solve, args.steps, tag="solve", align=world > 1)
         sim.sync()
         # keep the device loaded until NVML has a few samples even if the timed region is short
         # (single GPU only: on slabs every solve is a collective, so all ranks must issue the
@@ -429,6 +446,8 @@ def main():
     cfgd = workload_config(world, transport, strong_main)
     if world > 1:
         cfgd["halo"] = f"{ITERS + 1} rows of p + {ITERS} of div per neighbour per solve, transport {transport}"
+        cfgd["rank_alignment"] = ("one untimed solve (a neighbour-collective) between the barrier and the start event lines the "
+                                  "ranks up on the device; the K timed solves follow it, max over ranks")
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -477,7 +496,7 @@ def main():
         ssolve = lambda: ssim.pass_("pressure_solve")
         for _ in range(args.warmup): ssolve()
         ssim.sync(); dist.barrier()
-        sms = time_steps(ssim, ssolve, args.steps); ssim.sync()
+        sms = time_steps(ssim, ssolve, args.steps, align=True); ssim.sync()
         t = torch.tensor([sms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); sms = float(t.item())
         out["strong"] = {"value": W * args.grid * ITERS * args.steps / (sms * 1e-3), "unit": UNIT, "ms_per_step": sms / args.steps,
                          "grid": f"ONE {W}x{args.grid} grid split into {world} row slabs of {srows} rows", "steps": args.steps,
