@@ -109,6 +109,30 @@ def main():
             pass
     out += ["```", "averages per exchange: `wait-free` = until the neighbour released its ghost rows (pure rank skew: the faster GPU waits),",
             "`push` = first store to \"ready\" published, `wait-ready` = until the neighbour's rows have arrived.", ""]
+    out += ["Caveat found after call 14: these are averages over ALL exchanges of the process, the first one included, and the first",
+            "exchange after a barrier absorbs whatever host-side skew the ranks have at that moment (hundreds of microseconds to",
+            "milliseconds, see the `exchanges 3` lines) — the 10 us `wait-free` of the 210-exchange line is mostly that one event.", ""]
+    out += ["## 4b. Reading the N >= 4 numbers of call 14: a constant stall per run, not a cost per solve", "",
+            "The call-14 numbers at N = 4 and 8 are far off round 1's (weak N=8: 0.436 vs 0.319 ms; 8192²/40 on 8 GPUs: 1.53 vs 0.21 ms;",
+            "16384²/80 on 8: 16.3 vs 1.11 ms) although the exchange schedule is the same and N=2 is unchanged.  Multiplying the excess per",
+            "solve by the number of timed solves gives the same few tens of milliseconds whatever the workload:", "",
+            "| run (call 14) | timed solves | ms / solve | expected (round 1 / ideal) | excess x solves |", "|---|---|---|---|---|",
+            "| weak N=8 | 200 | 0.4356 | ~0.27 | ~33 ms |", "| weak N=8, NCCL | 200 | 0.4404 | ~0.29 | ~30 ms |", "| weak N=4 | 200 | 0.3359 | ~0.27 | ~13 ms |",
+            "| strong 4096², N=8, --quick | 200 | 0.3156 | 0.127 (round 1) | ~38 ms |",
+            "| strong 4096², N=8, `strong` block of the weak-8 run (same box, same workload) | 200 | 0.2225 | 0.127 | ~19 ms |",
+            "| strong 8192²/40, N=8 | 50 | 1.5349 | 0.213 (round 1) | ~66 ms |", "| strong 8192²/40, N=4 | 50 | 0.5651 | ~0.2 | ~18 ms |",
+            "| strong 16384²/80, N=8 | 5 | 16.303 | 1.11 (round 1) | ~76 ms |", "",
+            "A per-solve cost would scale with `--steps`; this does not (and the same workload measured twice on the same box differs by",
+            "19 ms in total).  It is one stall of 15-75 ms per run, growing with the number of processes: between the barrier and the",
+            "start event every rank ran `nvmlInit()` + handle look-ups for the clock sampler — with 8 processes on one box these",
+            "serialise inside the driver, the last rank enters its timed loop tens of milliseconds after the first, and its neighbours",
+            "(whose start events are already recorded) spin in the first halo exchange waiting for it, inside their device timers.",
+            "`bench.py` now initialises NVML before the warm-up, polls on rank 0 only, and issues one untimed solve (a collective",
+            "between neighbours) between the barrier and the start event so that the ranks are lined up on the device when timing",
+            "starts.  The GPU budget of the round was spent by call 14 itself (11 minutes on 8 GPUs), so the corrected numbers are the",
+            "driver's end-of-round N = 1, 2, 4, 8 runs, not in this file.  What call 14 does establish at N = 8: bitwise parity of",
+            "all slabs with a single-GPU run after three successive solves (peer-memory path), `slab_check` of full steps, and that",
+            "both transports and the mirrored path complete.", ""]
     try:
         out += ["## 5. Slab parity runs", "", "```"]
         for f in ("c10_slab_check.log", "c13_slab_check.log", "c14_slab_check.log"):
