@@ -37,6 +37,31 @@ def jacobi_launches(iters: int, block: int = DEFAULT_BLOCK) -> list[int]:
     return [base + (1 if k < extra else 0) for k in range(n)]
 
 
+def host_bands(sim_h: int, iters: int, bands: int = 16, block: int = DEFAULT_BLOCK) -> list[dict]:
+    """Plan of `fluid_pressure_solve_host` on one GPU (fluid.cu solve_host_banded): the grid is cut into row
+    bands; band b is solved as soon as upload chunk b has arrived and is downloaded while later chunks upload.
+    Returns one dict per band: owned rows [lo, hi), upload chunk [up_lo, up_hi) (what the band needs beyond the
+    earlier chunks: rows up to hi + iters), and per launch (K, out_lo, out_hi) — launch k produces the band's
+    rows +- the sweeps still to come.  Empty list: the one-piece path (grid too short for two bands)."""
+    nb = min(bands, 16, sim_h // max(256, 4 * iters)) if iters > 0 else 0
+    if nb < 2:
+        return []
+    band = (sim_h + nb - 1) // nb
+    out = []
+    for b in range(nb):
+        lo = min(b * band, sim_h); hi = min(lo + band, sim_h)
+        if hi <= lo:
+            break
+        up_lo = 0 if b == 0 else min(lo + iters, sim_h)
+        up_hi = sim_h if hi == sim_h else min(hi + iters, sim_h)
+        launches, remaining = [], iters
+        for K in jacobi_launches(iters, block):
+            remaining -= K
+            launches.append((K, max(lo - remaining, 0), min(hi + remaining, sim_h)))
+        out.append(dict(lo=lo, hi=hi, up_lo=up_lo, up_hi=up_hi, launches=launches))
+    return out
+
+
 @dataclass
 class SlabPlan:
     sim_h: int
