@@ -431,7 +431,7 @@ int run_jacobi(fluid_t* h, int iters, bool scale_first, int* launches_out) {
     // launch 1 — the only rows of it that read ghost rows — go to a second stream, the interior rows
     // [row0+K1, row1-K1) of launch 1 run meanwhile on the compute stream.
     // Default OFF: measured on 2 B200 (4096 x 4096 per rank, 50 iterations) the split costs more than it hides —
-    // 0.310 ms per solve with it, 0.300 ms without (profiles/r02_scaling.md); FLUID_HALO_OVERLAP=1 enables it.
+    // 0.327 ms per solve with it, 0.277 ms without (same box, profiles/r02_scaling.md); FLUID_HALO_OVERLAP=1 enables it.
     static const bool overlap_off = !(getenv("FLUID_HALO_OVERLAP") && !strcmp(getenv("FLUID_HALO_OVERLAP"), "1"));
     const int K1 = base + (extra ? 1 : 0);
     const bool overlap = deep && blocked && !overlap_off && h->stream2 && (h->row1 - h->row0) >= 2 * K1 + 4 * K1;
