@@ -99,8 +99,9 @@ def peak_hbm():
 class ClockSampler:
     """Polls NVML for SM clock + throttle reasons while the timed region runs."""
 
-    def __init__(self, index, enabled=True):
+    def __init__(self, index, enabled=True, period=0.002):
         self.samples, self.reasons, self._stop = [], set(), threading.Event()
+        self.period = period
         self.max_mhz = None
         try:
             if not enabled:
@@ -133,7 +134,7 @@ class ClockSampler:
                         self.reasons.add(nm)
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(self.period)
 
     def __enter__(self):
         if self.nv:
@@ -379,7 +380,7 @@ def main():
     # NVML is initialised (and its polling thread started) BEFORE the warm-up and the barrier: nvmlInit with 8
     # processes on one box takes milliseconds, which must not sit between the barrier and the timed region.
     # Only rank 0 reports clocks, so only rank 0 polls.
-    with ClockSampler(local, enabled=(rank == 0)) as clk:
+    with ClockSampler(local, enabled=(rank == 0), period=0.002 if world == 1 else 0.005) as clk:
         for _ in range(args.warmup):
             solve()
         barrier()
